@@ -1,0 +1,106 @@
+// oracle/ref_video_harness.cpp — TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Drives the UNMODIFIED reference composite synthesiser (/root/reference/src/video.cpp,
+// linked with player.cpp/streamer.cpp/sbc_decoder.cpp for Frame and the OS shim) into
+// oracle/_ref/libefref_vid.so. Protocol = SURVEY.md §8c "Composite golden vectors":
+// video_init(std); copy an I420 frame into Frame fb[0] through get_y/get_cr/get_cb;
+// set the ISR's file-scope state; call video_isr() _line_count times with two alternating
+// line buffers; concatenate _line_width uint16 per line.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#include "player.h"   // reference headers: Frame, video_init, ...
+#undef printf
+
+static int g_quiet = 1;
+extern "C" int efref_putchar(int c) { if (!g_quiet) fputc(c, stderr); return c; }
+std::string to_string(int i) { return std::to_string(i); }
+
+// ESP-only hooks that the simulator build leaves undefined (video.cpp:309-313, 962)
+void video_init_hw(int, int) {}
+void ir_sample() {}
+void write_pcm_16(const int16_t*, int, int) {}
+
+// file-scope state of video.cpp (video.cpp:533-552, 936-949)
+extern volatile int _line_counter;
+extern volatile int _frame_counter;
+extern int _line_count, _line_width, _hsync, _hsync_long, _hsync_short, _burst_start, _burst_width, _active_start;
+extern int8_t _next_frame, _current_frame;
+extern int16_t _hscroll;
+extern Frame* _frames;
+extern uint32_t _color_tab[256 * 3];
+extern int16_t* _burst0;
+extern int16_t* _burst1;
+extern "C" void video_isr(volatile void* vbuf);
+void blit(Frame* frame, uint16_t* dst, int line, int x, int width);   // video.cpp:690 (not in video.h)
+
+static Frame* g_fb = nullptr;
+static int g_std = -1;
+
+static void load_i420(Frame* f, const uint8_t* s)
+{
+    for (int y = 0; y < 192; y++, s += 352) memcpy(f->get_y(y), s, 352);
+    for (int y = 0; y < 96; y++, s += 176) memcpy(f->get_cr(y), s, 176);
+    for (int y = 0; y < 96; y++, s += 176) memcpy(f->get_cb(y), s, 176);
+}
+
+extern "C" {
+
+void efref_set_quiet(int q) { g_quiet = q; }
+
+// video_init (video.cpp:572). ntsc=1 NTSC, 0 PAL. Safe to call again to switch standard.
+void efref_video_init(int ntsc)
+{
+    if (!g_fb) { g_fb = new Frame[2]; g_fb[0].init(); g_fb[1].init(); }
+    video_init(ntsc);
+    g_std = ntsc;
+}
+
+// geometry readback: [line_width, line_count, hsync, hsync_long, hsync_short, burst_start, burst_width, active_start]
+void efref_geometry(int* g)
+{
+    g[0] = _line_width; g[1] = _line_count; g[2] = _hsync; g[3] = _hsync_long;
+    g[4] = _hsync_short; g[5] = _burst_start; g[6] = _burst_width; g[7] = _active_start;
+}
+
+void efref_color_tab(uint32_t* dst) { memcpy(dst, _color_tab, sizeof(_color_tab)); }
+
+int efref_pal_burst(int16_t* b0, int16_t* b1)
+{
+    if (!_burst0) return 0;
+    memcpy(b0, _burst0, _burst_width * 2); memcpy(b1, _burst1, _burst_width * 2);
+    return _burst_width;
+}
+
+// One whole field via video_isr (video.cpp:1122). `i420` = frame shown (fb[0]); optional
+// `i420_b` = the other frame (fb[1]) used when hscroll != 0. Returns samples written.
+long efref_field(const uint8_t* i420, const uint8_t* i420_b, int frame_counter, int hscroll, uint16_t* out)
+{
+    load_i420(&g_fb[0], i420);
+    if (i420_b) load_i420(&g_fb[1], i420_b);
+    _frames = g_fb; _current_frame = 0; _next_frame = -1;
+    _line_counter = 0; _frame_counter = frame_counter; _hscroll = (int16_t)hscroll;
+    _video_composite_blend = 0;
+    uint16_t* lb[2];
+    lb[0] = (uint16_t*)calloc(_line_width + 64, 2);
+    lb[1] = (uint16_t*)calloc(_line_width + 64, 2);
+    int lines = _line_count, w = _line_width;
+    for (int l = 0; l < lines; l++) {
+        video_isr(lb[l & 1]);
+        memcpy(out + (size_t)l * w, lb[l & 1], (size_t)w * 2);
+    }
+    free(lb[0]); free(lb[1]);
+    return (long)lines * w;
+}
+
+// One blit() call (video.cpp:690) into a caller buffer: the north_star "line-blit entry point".
+void efref_blit(const uint8_t* i420, int frame_counter, uint16_t* dst, int line, int x, int width)
+{
+    load_i420(&g_fb[0], i420);
+    _frame_counter = frame_counter;
+    blit(&g_fb[0], dst, line, x, width);
+}
+
+}  // extern "C"
