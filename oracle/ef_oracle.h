@@ -1,0 +1,68 @@
+/* oracle/ef_oracle.h — CPU restatement of the espflix hot path. TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library;
+ * the product (espflix_b200/) never links, imports or calls it.
+ *
+ * Parity status: PINNED. The restatement reproduces, bit for bit, the I420 dumps and composite
+ * fields that the UNMODIFIED reference (oracle/_ref, built from /root/reference/src) produces for
+ * the reference's embedded media fixtures (tests/golden, decode_pins.json and composite_pins.json) and for the synthetic coverage
+ * streams (tests/test_oracle_vs_ref.py, run where /root/reference exists).
+ */
+#ifndef EF_ORACLE_H
+#define EF_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFO_FB_WIDTH   352
+#define EFO_FB_HEIGHT  192
+#define EFO_FB_STRIDE  528          /* video.h:32 FB_STRIDE */
+#define EFO_FRAME_BYTES (EFO_FB_STRIDE * EFO_FB_HEIGHT)   /* 12 strips x 8448 B, strips contiguous */
+#define EFO_I420_BYTES (352 * 192 * 3 / 2)
+
+/* MPEG-TS (188-byte packets, video PID 0x100) -> elementary stream, following
+ * MpegDecoder::more/demux (player.cpp:381-493). pes_off/pes_pts (optional, cap entries each)
+ * receive, per PES header seen on the video PID, the ES offset it starts at and its PTS (-1 if
+ * none). Returns ES byte count; *n_pes gets the PES count. */
+size_t efo_demux_ts(const uint8_t* ts, size_t len, uint8_t* es, size_t es_cap,
+                    uint64_t* pes_off, int64_t* pes_pts, size_t pes_cap, size_t* n_pes);
+
+/* Decode an elementary stream the way MpegDecoder::run does (player.cpp:1355), pushing frames
+ * as push_video would see them (player.cpp:692-702) and finishing with flush_picture(1).
+ * has_pts: 1 = every picture carries a PTS (normal TS input); 0 = none does (quirk Q10: no
+ * push, no buffer swap). Frames are written as I420 (SURVEY.md 8c layout) into out (cap frames).
+ * strips_out (optional): the two striped frame stores (2 x EFO_FRAME_BYTES) after the last picture.
+ * Returns the number of frames pushed. */
+long efo_decode_es(const uint8_t* es, size_t len, int has_pts,
+                   uint8_t* out_i420, size_t cap_frames, uint8_t* strips_out);
+
+/* TS convenience wrapper = efo_demux_ts + efo_decode_es (has_pts from the PES headers). */
+long efo_decode_ts(const uint8_t* ts, size_t len, uint8_t* out_i420, size_t cap_frames);
+
+/* The reference IDCT (player.cpp:922-996) on 64 prescaled int32 coefficients, in place. */
+void efo_idct(int32_t* b);
+
+/* I420 <-> striped frame store (video.h:36-44; player.cpp:33-46) */
+void efo_i420_to_strips(const uint8_t* i420, uint8_t* strips);
+void efo_strips_to_i420(const uint8_t* strips, uint8_t* i420);
+
+/* Composite synthesis (video.cpp:554-630, 690-934, 1122-1198). ntsc: 1 NTSC, 0 PAL. */
+typedef struct {
+    int ntsc, line_width, line_count, hsync, hsync_long, hsync_short, burst_start, burst_width, active_start;
+    uint32_t color_tab[768];
+    int16_t burst0[64], burst1[64];
+} efo_video;
+void efo_video_init(efo_video* v, int ntsc);
+/* one blit() call (video.cpp:690): frame in strips layout */
+void efo_blit(const efo_video* v, const uint8_t* strips, uint16_t* dst, int line, int x, int width, int frame_counter);
+/* whole field as video_isr would emit it line by line (two ping-pong line buffers, hscroll=0,
+ * no overlay); out = line_count x line_width uint16 */
+void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uint16_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
