@@ -1,0 +1,229 @@
+"""espflix_b200/capi.py — ctypes binding of include/espflix_b200.h. Fails loudly when the CUDA
+library is missing or no GPU is present: there is no CPU path in the product."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FRAME_BYTES = 101376
+I420_BYTES = 101376
+EF_OK, EF_EINVAL, EF_ECUDA, EF_ENOMEM, EF_ESTATE = 0, -1, -2, -3, -4
+
+
+class EspflixError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("espflix_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("n_streams", ctypes.c_int), ("max_pictures", ctypes.c_int),
+                ("max_slices_per_picture", ctypes.c_int), ("es_capacity", ctypes.c_size_t), ("fields", ctypes.c_int)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libespflix_b200.so")
+
+
+_lib = None
+_VP, _I, _U64P = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64)
+
+_SIGNATURES = {
+    "ef_last_error": (ctypes.c_char_p, []),
+    "ef_version": (ctypes.c_char_p, []),
+    "ef_create": (_I, [ctypes.POINTER(_VP), ctypes.POINTER(_Config)]),
+    "ef_destroy": (None, [_VP]),
+    "ef_reset": (_I, [_VP]),
+    "ef_submit_es_host": (_I, [_VP, _VP, _VP, _VP]),
+    "ef_submit_es_device": (_I, [_VP, _VP, _VP, _VP]),
+    "ef_submit_ts_host": (_I, [_VP, _VP, _VP, _VP]),
+    "ef_submit_ts_device": (_I, [_VP, _VP, _VP, _VP]),
+    "ef_index": (_I, [_VP, _VP]),
+    "ef_index_info": (_I, [_VP, ctypes.POINTER(_I), _U64P, _U64P, _U64P]),
+    "ef_stream_info": (_I, [_VP, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
+    "ef_decode_picture": (_I, [_VP, _I, _VP]),
+    "ef_decode_all": (_I, [_VP, _I, _VP]),
+    "ef_read_frame": (_I, [_VP, _I, _I, _VP]),
+    "ef_read_frame_i420": (_I, [_VP, _I, _I, _VP]),
+    "ef_write_frame_i420": (_I, [_VP, _I, _I, _VP]),
+    "ef_frame_device_ptr": (_I, [_VP, _I, _I, ctypes.POINTER(_VP)]),
+    "ef_read_latest_i420": (_I, [_VP, _I, _I, _VP, _VP]),
+    "ef_video_init": (_I, [_VP, _I]),
+    "ef_video_geometry": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
+    "ef_composite_field": (_I, [_VP, _I, _I, _VP]),
+    "ef_read_field": (_I, [_VP, _I, _VP]),
+    "ef_video_isr": (_I, [_VP, _I, _I, _VP]),
+    "ef_blit": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I]),
+    "ef_launch_count": (ctypes.c_uint64, [_VP]),
+}
+
+
+def load_library():
+    """Load libespflix_b200.so (built in-tree by __graft_entry__.build()). Raises if absent."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise EspflixError(EF_ECUDA, "CUDA library %s is not built (run __graft_entry__.build()); no CPU fallback exists" % p)
+        lib = ctypes.CDLL(p)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)          # raw (device) address
+
+
+class Context:
+    """One GPU's worth of independent decoders (see include/espflix_b200.h)."""
+
+    def __init__(self, n_streams, max_pictures=12, max_slices_per_picture=12, es_capacity=None, device=0, fields=True):
+        self.lib = load_library()
+        if es_capacity is None:
+            es_capacity = n_streams * max_pictures * 32768
+        cfg = _Config(device, n_streams, max_pictures, max_slices_per_picture, es_capacity, 1 if fields else 0)
+        self._h = _VP()
+        self.n_streams, self.max_pictures = n_streams, max_pictures
+        self._check(self.lib.ef_create(ctypes.byref(self._h), ctypes.byref(cfg)))
+
+    def _check(self, rc):
+        if rc != EF_OK:
+            raise EspflixError(rc, self.lib.ef_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self._h:
+            self.lib.ef_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._check(self.lib.ef_reset(self._h))
+
+    # -- submit -----------------------------------------------------------------------------
+    @staticmethod
+    def pack(streams):
+        """list of bytes-like -> (blob uint8 array, offsets uint64 array)"""
+        off = np.zeros(len(streams) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(s) for s in streams])
+        blob = np.frombuffer(b"".join(bytes(s) for s in streams), dtype=np.uint8).copy() if int(off[-1]) else np.zeros(1, np.uint8)
+        return blob, off
+
+    def submit_es(self, blob, off, stream=0, device=False):
+        fn = self.lib.ef_submit_es_device if device else self.lib.ef_submit_es_host
+        self._check(fn(self._h, _ptr(blob), _ptr(off), stream))
+
+    def submit_ts(self, blob, off, stream=0, device=False):
+        fn = self.lib.ef_submit_ts_device if device else self.lib.ef_submit_ts_host
+        self._check(fn(self._h, _ptr(blob), _ptr(off), stream))
+
+    def index(self, stream=0):
+        self._check(self.lib.ef_index(self._h, stream))
+
+    def index_info(self):
+        mp, tp, ts, eb = _I(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.ef_index_info(self._h, ctypes.byref(mp), ctypes.byref(tp), ctypes.byref(ts), ctypes.byref(eb)))
+        return {"max_pictures": mp.value, "total_pictures": tp.value, "total_slices": ts.value, "es_bytes": eb.value}
+
+    def stream_info(self, s):
+        a, b = _I(), _I()
+        self._check(self.lib.ef_stream_info(self._h, s, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    # -- decode -----------------------------------------------------------------------------
+    def decode_picture(self, pic, stream=0):
+        self._check(self.lib.ef_decode_picture(self._h, pic, stream))
+
+    def decode_all(self, n_pictures, stream=0):
+        self._check(self.lib.ef_decode_all(self._h, n_pictures, stream))
+
+    def read_frame(self, s, fb=-1):
+        out = np.empty(FRAME_BYTES, dtype=np.uint8)
+        self._check(self.lib.ef_read_frame(self._h, s, fb, out.ctypes.data))
+        return out
+
+    def read_frame_i420(self, s, fb=-1):
+        out = np.empty(I420_BYTES, dtype=np.uint8)
+        self._check(self.lib.ef_read_frame_i420(self._h, s, fb, out.ctypes.data))
+        return out
+
+    def write_frame_i420(self, s, fb, data):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert data.size == I420_BYTES
+        self._check(self.lib.ef_write_frame_i420(self._h, s, fb, data.ctypes.data))
+
+    def read_latest_i420(self, first=0, count=None, out=None, stream=0):
+        count = self.n_streams - first if count is None else count
+        if out is None:
+            out = np.empty((count, I420_BYTES), dtype=np.uint8)
+        self._check(self.lib.ef_read_latest_i420(self._h, first, count, _ptr(out), stream))
+        return out
+
+    def frame_device_ptr(self, s, fb):
+        p = _VP()
+        self._check(self.lib.ef_frame_device_ptr(self._h, s, fb, ctypes.byref(p)))
+        return p.value
+
+    def decode_sequence(self, streams, ts=False):
+        """Convenience used by the parity tests: submit, index, then decode picture by picture,
+        returning for every stream the list of I420 frames in presentation (push_video) order."""
+        blob, off = self.pack(streams)
+        (self.submit_ts if ts else self.submit_es)(blob, off)
+        self.index()
+        info = self.index_info()
+        frames = [[] for _ in streams]
+        counts = [self.stream_info(i)[0] for i in range(len(streams))]
+        for p in range(info["max_pictures"]):
+            self.decode_picture(p)
+            for i in range(len(streams)):
+                if p < counts[i]:
+                    base = self.stream_info(i)[1]
+                    frames[i].append(self.read_frame_i420(i, (base + p + 1) & 1))
+        return frames
+
+    # -- composite --------------------------------------------------------------------------
+    def video_init(self, ntsc):
+        self._check(self.lib.ef_video_init(self._h, 1 if ntsc else 0))
+
+    def geometry(self):
+        w, n = _I(), _I()
+        self._check(self.lib.ef_video_geometry(self._h, ctypes.byref(w), ctypes.byref(n)))
+        return w.value, n.value
+
+    def composite_field(self, fb=-1, frame_counter=0, stream=0):
+        self._check(self.lib.ef_composite_field(self._h, fb, frame_counter, stream))
+
+    def read_field(self, s):
+        w, n = self.geometry()
+        out = np.empty(w * n, dtype=np.uint16)
+        self._check(self.lib.ef_read_field(self._h, s, out.ctypes.data))
+        return out
+
+    def video_isr(self, s, line):
+        w, _ = self.geometry()
+        out = np.empty(w, dtype=np.uint16)
+        self._check(self.lib.ef_video_isr(self._h, s, line, out.ctypes.data))
+        return out
+
+    def blit(self, s, fb, line, x, width, frame_counter, dst=None):
+        if dst is None:
+            dst = np.zeros(2 * 352 + 160, dtype=np.uint16)
+        self._check(self.lib.ef_blit(self._h, s, fb, dst.ctypes.data, line, x, width, frame_counter))
+        return dst
+
+    def launch_count(self):
+        return int(self.lib.ef_launch_count(self._h))

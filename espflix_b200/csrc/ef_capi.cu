@@ -1,0 +1,530 @@
+// espflix_b200/csrc/ef_capi.cu — the C-ABI of libespflix_b200.so (include/espflix_b200.h).
+// Context management, submits, launches and read-back. No CPU fallback: every path goes through
+// the CUDA kernels in ef_index.cu / ef_decode.cu / ef_composite.cu or fails with EF_ECUDA.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/espflix_b200.h"
+#include "ef_common.cuh"
+
+// from the other translation units
+int ef_build_tables(EfTables* t);
+void ef_build_color_tab(uint32_t* tab768, int ntsc);
+void ef_build_pal_burst(int16_t* b0, int16_t* b1, int width);
+cudaError_t ef_index_upload_constants();
+const unsigned char* ef_default_intra_ptr();
+__global__ void ef_scan_kernel(EfDev* Dp);
+__global__ void ef_prefix_kernel(EfDev* Dp);
+__global__ void ef_fill_kernel(EfDev* Dp);
+__global__ void ef_ts_len_kernel(const uint8_t* ts, uint64_t n_packets, uint32_t* out_len);
+__global__ void ef_ts_copy_kernel(const uint8_t* ts, uint64_t n_packets, const uint64_t* out_off, uint8_t* es);
+__global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint64_t* off, const uint64_t* ts_off, int n_streams, uint64_t* es_off);
+size_t ef_decode_smem_bytes();
+cudaError_t ef_decode_configure();
+cudaError_t ef_launch_decode(const EfDev* dev, int pic, int ctas, cudaStream_t stream);
+cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, cudaStream_t stream);
+cudaError_t ef_launch_blit(const EfDev* dev, int stream_index, int fb, int line, int x, int width, int frame_counter, uint16_t* dst, cudaStream_t stream);
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(EF_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// strips layout <-> I420 (video.h:36-44; player.cpp:33-46) — device kernels so that reads stay one copy
+__global__ void ef_strips_to_i420_kernel(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ base_pics,
+                                         const uint32_t* __restrict__ n_pics, int first, int count, int fb_sel, uint8_t* __restrict__ dst)
+{
+    // one thread per 4 output bytes
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t per = EF_FRAME / 4;
+    const uint32_t k = (uint32_t)(t / per), w = (uint32_t)(t % per);
+    if (k >= (uint32_t)count) return;
+    const int s = first + (int)k;
+    const int fb = fb_sel >= 0 ? fb_sel : (int)((base_pics[s] + n_pics[s]) & 1u);
+    const uint8_t* f = frames + ef_frame_offset(s, fb);
+    const uint32_t b = w * 4;
+    uint32_t src;
+    if (b < EF_W * EF_H) { const uint32_t y = b / EF_W, x = b % EF_W; src = y * EF_STRIDE + x; }
+    else {
+        const uint32_t c = b - EF_W * EF_H;
+        const uint32_t plane = c / (176 * 96), r = c % (176 * 96);
+        const uint32_t y = r / 176, x = r % 176;
+        src = (y >> 3) * 8448 + ((y & 7) + plane * 8) * EF_STRIDE + EF_W + x;
+    }
+    *(uint32_t*)(dst + (size_t)k * EF_FRAME + b) = *(const uint32_t*)(f + src);
+}
+
+__global__ void ef_i420_to_strips_kernel(uint8_t* __restrict__ frame, const uint8_t* __restrict__ src)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= EF_FRAME / 4) return;
+    const uint32_t b = w * 4;
+    uint32_t dst;
+    if (b < EF_W * EF_H) { const uint32_t y = b / EF_W, x = b % EF_W; dst = y * EF_STRIDE + x; }
+    else {
+        const uint32_t c = b - EF_W * EF_H;
+        const uint32_t plane = c / (176 * 96), r = c % (176 * 96);
+        const uint32_t y = r / 176, x = r % 176;
+        dst = (y >> 3) * 8448 + ((y & 7) + plane * 8) * EF_STRIDE + EF_W + x;
+    }
+    *(uint32_t*)(frame + dst) = *(const uint32_t*)(src + b);
+}
+
+__global__ void ef_reset_seq_kernel(EfDev* Dp, const uint8_t* default_intra)
+{
+    EfDev& D = *Dp;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= D.n_streams) return;
+    EfSeq* q = D.seq + (size_t)s * (D.max_seq + 1);
+    for (int e = 0; e < 64; e++) {
+        const int t = (e & 7) * 8 + (e >> 3);
+        q->intra_qT[t] = default_intra[e];
+        q->inter_qT[t] = 16;
+    }
+    q->mb_width = 22; q->mb_height = 12; q->valid = 1; q->pad0 = 0;
+    D.n_pics[s] = 0; D.base_pics[s] = 0; D.n_seq[s] = 0;
+}
+
+}  // namespace
+
+struct ef_ctx {
+    ef_config cfg;
+    int sm_count = 0;
+    EfDev h;                   // host copy of the device context
+    EfDev* d = nullptr;
+    std::vector<void*> allocs;
+    uint8_t* d_es = nullptr;  // owned ES buffer (es_capacity + 64)
+    uint64_t* d_es_off = nullptr;
+    uint8_t* d_ts = nullptr;  // TS staging (same capacity) + packet tables, allocated on first TS submit
+    uint32_t* d_pkt_len = nullptr;
+    uint64_t* d_pkt_off = nullptr;
+    uint64_t* d_ts_off = nullptr;
+    uint8_t* d_stage = nullptr;      // read-back staging (I420 / strips)
+    size_t stage_bytes = 0;
+    uint8_t* d_default_intra = nullptr;
+    uint32_t* d_color_tab = nullptr;
+    int16_t* d_pal_burst = nullptr;
+    bool indexed = false, submitted = false, video = false;
+    uint64_t launches = 0;
+    uint64_t es_bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(ef_ctx* c, T** p, size_t n)
+{
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, n * sizeof(T) + 256);
+    if (e != cudaSuccess) return fail(EF_ECUDA, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    c->allocs.push_back(v);
+    *p = (T*)v;
+    return EF_OK;
+}
+
+int ensure_stage(ef_ctx* c, size_t bytes)
+{
+    if (c->stage_bytes >= bytes) return EF_OK;
+    void* v = nullptr;
+    CK(cudaMalloc(&v, bytes));
+    c->allocs.push_back(v);
+    c->d_stage = (uint8_t*)v; c->stage_bytes = bytes;
+    return EF_OK;
+}
+
+int resolve_fb(ef_ctx* c, int stream_index, int fb, int* out)
+{
+    if (stream_index < 0 || stream_index >= c->cfg.n_streams) return fail(EF_EINVAL, "stream index %d out of range", stream_index);
+    if (fb == 0 || fb == 1) { *out = fb; return EF_OK; }
+    if (fb != -1) return fail(EF_EINVAL, "fb must be 0, 1 or -1");
+    uint32_t a = 0, b = 0;
+    CK(cudaMemcpy(&a, c->h.base_pics + stream_index, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&b, c->h.n_pics + stream_index, 4, cudaMemcpyDeviceToHost));
+    *out = (int)((a + b) & 1u);
+    return EF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ef_last_error(void) { return g_err; }
+const char* ef_version(void) { return "espflix_b200 0.1 (sm_100a)"; }
+
+int ef_create(ef_ctx** out, const ef_config* cfg)
+{
+    if (!out || !cfg) return fail(EF_EINVAL, "null argument");
+    if (cfg->n_streams < 1 || cfg->max_pictures < 1 || cfg->max_slices_per_picture < 1 || cfg->es_capacity < 16)
+        return fail(EF_EINVAL, "bad config (n_streams=%d max_pictures=%d max_slices_per_picture=%d es_capacity=%zu)",
+                    cfg->n_streams, cfg->max_pictures, cfg->max_slices_per_picture, cfg->es_capacity);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= cfg->device)
+        return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", cfg->device, cudaGetErrorString(e));
+    CK(cudaSetDevice(cfg->device));
+    ef_ctx* c = new ef_ctx();
+    c->cfg = *cfg;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    c->sm_count = prop.multiProcessorCount;
+    if ((size_t)prop.sharedMemPerBlockOptin < ef_decode_smem_bytes()) {
+        delete c;
+        return fail(EF_ECUDA, "device offers %zu B shared memory per CTA, kernel needs %zu", (size_t)prop.sharedMemPerBlockOptin, ef_decode_smem_bytes());
+    }
+    CK(ef_decode_configure());
+    CK(ef_index_upload_constants());
+
+    const int n = cfg->n_streams;
+    EfDev& h = c->h;
+    memset(&h, 0, sizeof(h));
+    h.n_streams = n; h.max_pictures = cfg->max_pictures;
+    h.max_slices = cfg->max_pictures * cfg->max_slices_per_picture;
+    h.max_seq = cfg->max_pictures;
+    int rc;
+#define A(ptr, count) if ((rc = dev_alloc(c, &(ptr), (count))) != EF_OK) { ef_destroy(c); return rc; }
+    A(c->d_es, cfg->es_capacity + 64);
+    A(c->d_es_off, (size_t)n + 1);
+    A(h.frames, (size_t)n * 2 * EF_FRAME + 1024);
+    A(h.seq, (size_t)n * (h.max_seq + 1));
+    A(h.pics, (size_t)n * h.max_pictures);
+    A(h.slice_off, (size_t)n * h.max_slices);
+    A(h.slice_code, (size_t)n * h.max_slices);
+    A(h.n_pics, n); A(h.base_pics, n); A(h.n_seq, n);
+    A(h.pic_pref, (size_t)n * h.max_pictures);
+    A(h.pic_total, h.max_pictures); A(h.pic_base, h.max_pictures); A(h.cursor, h.max_pictures);
+    h.work_capacity = (size_t)n * h.max_slices;
+    A(h.work, h.work_capacity);
+    A(h.info, 8);
+    EfTables* dt; A(dt, 1);
+    A(c->d_color_tab, 768); A(c->d_pal_burst, 128); A(c->d_default_intra, 64);
+    if (cfg->fields) { h.field_stride = EF_PAL_FIELD_SAMPLES; A(h.fields, (size_t)n * h.field_stride); }
+    A(c->d, 1);
+#undef A
+    h.es = c->d_es; h.es_off = c->d_es_off; h.tables = dt;
+    h.color_tab = c->d_color_tab; h.pal_burst = c->d_pal_burst;
+
+    EfTables t;
+    const int bad = ef_build_tables(&t);
+    if (bad) { ef_destroy(c); return fail(EF_EINVAL, "internal: VLC table %d does not fit its lookup shape", bad); }
+    CK(cudaMemcpy(dt, &t, sizeof(t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_default_intra, ef_default_intra_ptr(), 64, cudaMemcpyHostToDevice));
+    CK(cudaMemset(c->d_es, 0, cfg->es_capacity + 64));
+    CK(cudaMemset(c->d_es_off, 0, ((size_t)n + 1) * 8));
+    CK(cudaMemcpy(c->d, &h, sizeof(h), cudaMemcpyHostToDevice));
+    *out = c;
+    rc = ef_reset(c);
+    if (rc != EF_OK) { ef_destroy(c); *out = nullptr; return rc; }
+    rc = ef_video_init(c, 1);
+    if (rc != EF_OK) { ef_destroy(c); *out = nullptr; return rc; }
+    return EF_OK;
+}
+
+void ef_destroy(ef_ctx* c)
+{
+    if (!c) return;
+    cudaDeviceSynchronize();
+    for (void* p : c->allocs) cudaFree(p);
+    delete c;
+}
+
+int ef_reset(ef_ctx* c)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    CK(cudaMemset(c->h.frames, 0, (size_t)c->cfg.n_streams * 2 * EF_FRAME + 1024));     // Frame::init zero-fills (player.cpp:25)
+    ef_reset_seq_kernel<<<(c->cfg.n_streams + 127) / 128, 128>>>(c->d, c->d_default_intra);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemset(c->h.info, 0, 32));
+    CK(cudaDeviceSynchronize());
+    c->indexed = false; c->submitted = false;
+    return EF_OK;
+}
+
+static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, bool host, bool ts, cudaStream_t st)
+{
+    if (!c || !src || !off) return fail(EF_EINVAL, "null argument");
+    const int n = c->cfg.n_streams;
+    std::vector<uint64_t> hoff((size_t)n + 1);
+    if (host) memcpy(hoff.data(), off, ((size_t)n + 1) * 8);
+    else { CK(cudaMemcpyAsync(hoff.data(), off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    const uint64_t total = hoff[n];
+    if (total > c->cfg.es_capacity) return fail(EF_ENOMEM, "submit of %llu bytes exceeds es_capacity %zu", (unsigned long long)total, c->cfg.es_capacity);
+    for (int i = 0; i < n; i++) if (hoff[i] > hoff[i + 1]) return fail(EF_EINVAL, "stream offsets must be non-decreasing");
+    const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (!ts) {
+        CK(cudaMemcpyAsync(c->d_es, src, total, kind, st));
+        CK(cudaMemsetAsync(c->d_es + total, 0, 64, st));
+        CK(cudaMemcpyAsync(c->d_es_off, hoff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));          // hoff is a local
+        c->es_bytes = total;
+    } else {
+        for (int i = 0; i <= n; i++) if (hoff[i] % 188) return fail(EF_EINVAL, "TS stream offsets must be multiples of 188");
+        const uint64_t n_packets = total / 188;
+        if (!c->d_ts) {
+            int rc;
+            if ((rc = dev_alloc(c, &c->d_ts, c->cfg.es_capacity + 64)) != EF_OK) return rc;
+            if ((rc = dev_alloc(c, &c->d_pkt_len, c->cfg.es_capacity / 188 + 1)) != EF_OK) return rc;
+            if ((rc = dev_alloc(c, &c->d_pkt_off, c->cfg.es_capacity / 188 + 1)) != EF_OK) return rc;
+            if ((rc = dev_alloc(c, &c->d_ts_off, (size_t)n + 1)) != EF_OK) return rc;
+        }
+        CK(cudaMemcpyAsync(c->d_ts, src, total, kind, st));
+        CK(cudaMemcpyAsync(c->d_ts_off, hoff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (n_packets) {
+            ef_ts_len_kernel<<<(unsigned)((n_packets + 255) / 256), 256, 0, st>>>(c->d_ts, n_packets, c->d_pkt_len);
+            CK(cudaGetLastError());
+            ef_ts_scan_kernel<<<1, 1024, 0, st>>>(c->d_pkt_len, n_packets, c->d_pkt_off, c->d_ts_off, n, c->d_es_off);
+            CK(cudaGetLastError());
+            ef_ts_copy_kernel<<<(unsigned)((n_packets * 32 + 255) / 256), 256, 0, st>>>(c->d_ts, n_packets, c->d_pkt_off, c->d_es);
+            CK(cudaGetLastError());
+            c->launches += 3;
+        } else CK(cudaMemsetAsync(c->d_es_off, 0, ((size_t)n + 1) * 8, st));
+        CK(cudaStreamSynchronize(st));
+        c->es_bytes = total;                    // upper bound; exact ES size is on the device
+    }
+    c->submitted = true; c->indexed = false;
+    return EF_OK;
+}
+
+int ef_submit_es_host(ef_ctx* c, const uint8_t* es, const uint64_t* off, void* stream) { return submit_common(c, es, off, true, false, (cudaStream_t)stream); }
+int ef_submit_es_device(ef_ctx* c, const uint8_t* es, const uint64_t* off, void* stream) { return submit_common(c, es, off, false, false, (cudaStream_t)stream); }
+int ef_submit_ts_host(ef_ctx* c, const uint8_t* ts, const uint64_t* off, void* stream) { return submit_common(c, ts, off, true, true, (cudaStream_t)stream); }
+int ef_submit_ts_device(ef_ctx* c, const uint8_t* ts, const uint64_t* off, void* stream) { return submit_common(c, ts, off, false, true, (cudaStream_t)stream); }
+
+int ef_index(ef_ctx* c, void* stream)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (!c->submitted) return fail(EF_ESTATE, "ef_index before any submit");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = c->cfg.n_streams;
+    CK(cudaMemsetAsync(c->h.info, 0, 32, st));
+    ef_scan_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(c->d);
+    CK(cudaGetLastError());
+    ef_prefix_kernel<<<1, 1024, 0, st>>>(c->d);
+    CK(cudaGetLastError());
+    const size_t threads = (size_t)n * c->h.max_pictures;
+    ef_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->d);
+    CK(cudaGetLastError());
+    c->launches += 3;
+    c->indexed = true;
+    return EF_OK;
+}
+
+int ef_index_info(ef_ctx* c, int* max_pictures, uint64_t* total_pictures, uint64_t* total_slices, uint64_t* es_bytes)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (!c->indexed) return fail(EF_ESTATE, "ef_index_info before ef_index");
+    uint32_t info[8];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(info, c->h.info, 32, cudaMemcpyDeviceToHost));
+    if (max_pictures) *max_pictures = (int)info[0];
+    if (total_pictures) *total_pictures = info[1];
+    if (total_slices) *total_slices = info[2];
+    if (es_bytes) {
+        uint64_t last = 0;
+        CK(cudaMemcpy(&last, c->d_es_off + c->cfg.n_streams, 8, cudaMemcpyDeviceToHost));
+        *es_bytes = last;
+    }
+    if (info[3]) return fail(EF_ENOMEM, "index overflow (flags %u): raise max_pictures / max_slices_per_picture", info[3]);
+    return EF_OK;
+}
+
+int ef_stream_info(ef_ctx* c, int stream_index, int* n_pictures, int* base_pictures)
+{
+    if (!c || stream_index < 0 || stream_index >= c->cfg.n_streams) return fail(EF_EINVAL, "bad stream index");
+    uint32_t a = 0, b = 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&a, c->h.n_pics + stream_index, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&b, c->h.base_pics + stream_index, 4, cudaMemcpyDeviceToHost));
+    if (n_pictures) *n_pictures = (int)a;
+    if (base_pictures) *base_pictures = (int)b;
+    return EF_OK;
+}
+
+int ef_decode_picture(ef_ctx* c, int pic, void* stream)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (!c->indexed) return fail(EF_ESTATE, "ef_decode_picture before ef_index");
+    if (pic < 0 || pic >= c->cfg.max_pictures) return fail(EF_EINVAL, "picture index %d out of range", pic);
+    CK(ef_launch_decode(c->d, pic, c->sm_count, (cudaStream_t)stream));
+    c->launches++;
+    return EF_OK;
+}
+
+int ef_decode_all(ef_ctx* c, int n_pictures, void* stream)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (n_pictures < 0 || n_pictures > c->cfg.max_pictures) return fail(EF_EINVAL, "n_pictures %d out of range", n_pictures);
+    for (int p = 0; p < n_pictures; p++) {
+        int rc = ef_decode_picture(c, p, stream);
+        if (rc != EF_OK) return rc;
+    }
+    return EF_OK;
+}
+
+int ef_read_frame(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
+{
+    if (!c || !dst) return fail(EF_EINVAL, "null argument");
+    CK(cudaDeviceSynchronize());
+    int f; int rc = resolve_fb(c, stream_index, fb, &f);
+    if (rc != EF_OK) return rc;
+    CK(cudaMemcpy(dst, c->h.frames + ef_frame_offset(stream_index, f), EF_FRAME, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
+
+int ef_read_latest_i420(ef_ctx* c, int first, int count, uint8_t* dst, void* stream)
+{
+    if (!c || !dst) return fail(EF_EINVAL, "null argument");
+    if (first < 0 || count < 1 || first + count > c->cfg.n_streams) return fail(EF_EINVAL, "stream range out of bounds");
+    int rc = ensure_stage(c, (size_t)count * EF_FRAME);
+    if (rc != EF_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t threads = (uint64_t)count * (EF_FRAME / 4);
+    ef_strips_to_i420_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, c->d_stage);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemcpyAsync(dst, c->d_stage, (size_t)count * EF_FRAME, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return EF_OK;
+}
+
+int ef_read_frame_i420(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
+{
+    if (!c || !dst) return fail(EF_EINVAL, "null argument");
+    CK(cudaDeviceSynchronize());
+    int f; int rc = resolve_fb(c, stream_index, fb, &f);
+    if (rc != EF_OK) return rc;
+    rc = ensure_stage(c, EF_FRAME);
+    if (rc != EF_OK) return rc;
+    ef_strips_to_i420_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, c->d_stage);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemcpy(dst, c->d_stage, EF_FRAME, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
+
+int ef_write_frame_i420(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
+{
+    if (!c || !src) return fail(EF_EINVAL, "null argument");
+    int f; int rc = resolve_fb(c, stream_index, fb, &f);
+    if (rc != EF_OK) return rc;
+    rc = ensure_stage(c, EF_FRAME);
+    if (rc != EF_OK) return rc;
+    CK(cudaMemcpy(c->d_stage, src, EF_FRAME, cudaMemcpyHostToDevice));
+    ef_i420_to_strips_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames + ef_frame_offset(stream_index, f), c->d_stage);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaDeviceSynchronize());
+    return EF_OK;
+}
+
+int ef_frame_device_ptr(ef_ctx* c, int stream_index, int fb, void** ptr)
+{
+    if (!c || !ptr || stream_index < 0 || stream_index >= c->cfg.n_streams || (fb != 0 && fb != 1)) return fail(EF_EINVAL, "bad argument");
+    *ptr = c->h.frames + ef_frame_offset(stream_index, fb);
+    return EF_OK;
+}
+
+int ef_video_init(ef_ctx* c, int ntsc)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    EfGeometry g;
+    memset(&g, 0, sizeof(g));
+    g.ntsc = ntsc ? 1 : 0;
+    if (g.ntsc) {      // video_init(), video.cpp:572-600 (values probe-verified: tests/golden/composite_pins.json)
+        g.line_width = 912; g.line_count = 262; g.hsync = 64; g.hsync_long = 840; g.active_start = 144;
+        g.active_top = 32; g.vsync_start = 259; g.blit_start = g.active_start + 16;
+    } else {           // pal_init(), video.cpp:607-630
+        g.line_width = 1136; g.line_count = 312; g.hsync = 80; g.hsync_short = 32; g.hsync_long = 536;
+        g.burst_start = 96; g.burst_width = 44; g.active_start = 184;
+        g.active_top = 64; g.vsync_start = 304; g.blit_start = g.active_start + 16 + 80;
+    }
+    uint32_t tab[768];
+    int16_t burst[128];
+    memset(burst, 0, sizeof(burst));
+    ef_build_color_tab(tab, g.ntsc);
+    ef_build_pal_burst(burst, burst + 64, 44);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(c->d_color_tab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_pal_burst, burst, sizeof(burst), cudaMemcpyHostToDevice));
+    c->h.geo = g;
+    CK(cudaMemcpy(c->d, &c->h, sizeof(EfDev), cudaMemcpyHostToDevice));
+    c->video = true;
+    return EF_OK;
+}
+
+int ef_video_geometry(ef_ctx* c, int* line_width, int* line_count)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (line_width) *line_width = c->h.geo.line_width;
+    if (line_count) *line_count = c->h.geo.line_count;
+    return EF_OK;
+}
+
+int ef_composite_field(ef_ctx* c, int fb, int frame_counter, void* stream)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (!c->h.fields) return fail(EF_ESTATE, "context was created without field buffers (ef_config.fields = 0)");
+    if (fb < -1 || fb > 1) return fail(EF_EINVAL, "fb must be 0, 1 or -1");
+    CK(ef_launch_composite(c->d, c->cfg.n_streams, c->h.geo, fb, frame_counter, (cudaStream_t)stream));
+    c->launches++;
+    return EF_OK;
+}
+
+int ef_read_field(ef_ctx* c, int stream_index, uint16_t* dst)
+{
+    if (!c || !dst || stream_index < 0 || stream_index >= c->cfg.n_streams) return fail(EF_EINVAL, "bad argument");
+    if (!c->h.fields) return fail(EF_ESTATE, "no field buffers");
+    CK(cudaDeviceSynchronize());
+    const size_t n = (size_t)c->h.geo.line_width * c->h.geo.line_count;
+    CK(cudaMemcpy(dst, c->h.fields + (size_t)stream_index * c->h.field_stride, n * 2, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
+
+int ef_video_isr(ef_ctx* c, int stream_index, int line, uint16_t* buf)
+{
+    if (!c || !buf || stream_index < 0 || stream_index >= c->cfg.n_streams) return fail(EF_EINVAL, "bad argument");
+    if (!c->h.fields) return fail(EF_ESTATE, "no field buffers");
+    if (line < 0 || line >= c->h.geo.line_count) return fail(EF_EINVAL, "line %d out of range", line);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(buf, c->h.fields + (size_t)stream_index * c->h.field_stride + (size_t)line * c->h.geo.line_width,
+                  (size_t)c->h.geo.line_width * 2, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
+
+int ef_blit(ef_ctx* c, int stream_index, int fb, uint16_t* dst, int line, int x, int width, int frame_counter)
+{
+    if (!c || !dst) return fail(EF_EINVAL, "null argument");
+    if (line < 0 || line >= EF_H || x < 0 || width < 0 || (x & ~3) + width > EF_W) return fail(EF_EINVAL, "blit span out of range");
+    int f; int rc = resolve_fb(c, stream_index, fb, &f);
+    if (rc != EF_OK) return rc;
+    const int w8 = (width + 7) & ~7;          // the reference loop advances 8 pixels per iteration (video.cpp:709)
+    if (!w8) return EF_OK;
+    rc = ensure_stage(c, EF_FRAME);
+    if (rc != EF_OK) return rc;
+    CK(ef_launch_blit(c->d, stream_index, f, line, x, w8, frame_counter, (uint16_t*)c->d_stage, 0));
+    c->launches++;
+    // blit() itself offsets PAL output by 80 samples (video.cpp:698)
+    CK(cudaMemcpy(dst + (c->h.geo.ntsc ? 0 : 80), c->d_stage, (size_t)w8 * 4, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
+
+uint64_t ef_launch_count(ef_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// espflix_b200/csrc/ef_common.cuh — shared device/host definitions of libespflix_b200.so.
+//
+// HBM layout (one context = one GPU):
+//   es            [es_capacity + 64]            elementary streams of the current submit, back to back
+//   es_off        [n_streams + 1]  u64          byte offset of each stream in `es`
+//   frames        [n_streams][2][101,376]       the reference's two Frame stores per decoder
+//                                               (video.h:36-44). A Frame's 12 strips of 16 rows x 528 B
+//                                               are contiguous, so Y(x,y) = y*528 + x and the chroma
+//                                               columns 352..527 carry block-4 rows in strip rows 0-7
+//                                               and block-5 rows in strip rows 8-15 (player.cpp:33-46).
+//   seq           [n_streams][max_seq+1]        sequence-header state (quantiser matrices, mb_width/height);
+//                                               entry 0 = state carried in from the previous submit
+//   pics          [n_streams][max_pictures]     per picture: type, full_pel, r_size, seq index, first slice
+//   slices        [n_streams][max_slices]       per slice: byte offset after its start code, slice code
+//   work          [total slices]                flat per-picture slice work lists (K1's unit of work)
+//   fields        [n_streams][field samples]    composite output of K2 (u16)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define EF_W 352
+#define EF_H 192
+#define EF_STRIDE 528
+#define EF_FRAME 101376
+#define EF_MBW_MAX 22
+#define EF_MBH_MAX 12
+
+// ---- decode tables (built on the host by ef_tables.cpp from ISO 11172-2 Annex B) -------------
+// All VLC tables are indexed by (leading zeros, next 5 bits) so that one CLZ + one shared-memory
+// load decodes a symbol. Entry formats:
+//   dct:  bits 0-4 code length w/o sign (0 = invalid), 5-9 run, 10-15 level      [12][32] u16
+//   mba:  bits 0-3 length, 4-9 value (1..33, 34 stuffing, 35 escape)             [8][32]  u16
+//   mv:   bits 0-3 length (sign included), 4-9 value+16                          [7][32]  u16
+//   cbp:  bits 0-3 length, 4-9 pattern, indexed by the next 9 bits               [512]    u16
+//   ptype:bits 0-2 length, 3-7 macroblock_type flags, indexed by next 6 bits     [64]     u8
+struct EfTables {
+    uint16_t dct[12 * 32];
+    uint16_t mba[8 * 32];
+    uint16_t mv[7 * 32];
+    uint16_t cbp[512];
+    uint8_t ptype[64];
+    uint8_t izz[64];        // raster index -> zig-zag scan position
+    uint8_t prescale[64];   // AAN prescale, raster (reference scale_dct_q, player.cpp:161)
+    uint8_t pad[64];
+};
+
+// sequence state as the decode kernel reads it: matrices transposed ([col][row]) so that a lane
+// that owns one column of an 8x8 block fetches its 8 quantiser entries with one 8-byte load.
+struct __align__(16) EfSeq {
+    uint8_t intra_qT[64];
+    uint8_t inter_qT[64];
+    uint16_t mb_width, mb_height;
+    uint16_t valid, pad0;
+    uint32_t pad1[2];
+};
+
+struct __align__(16) EfPic {
+    uint32_t first_slice;   // index into the stream's slice list
+    uint32_t n_slices;
+    uint16_t seq;           // index into the stream's EfSeq table (0 = state carried over from the previous submit)
+    uint8_t type;           // picture_coding_type 1..4 (0 = none)
+    uint8_t fp_rsize;       // bit0 full_pel_forward, bits1-3 forward_r_size, as slice() will see them
+    uint32_t pad;
+};
+
+struct __align__(16) EfWork {   // one slice of one stream for one picture index
+    uint32_t stream;
+    uint32_t es_off;        // byte offset (relative to the stream start) of the first byte after the start code
+    uint32_t info;          // bits0-7 slice code, 8-10 picture type, 11 full_pel, 12-14 r_size, 16-31 seq index
+    uint32_t pad;
+};
+
+struct EfGeometry {          // video.cpp:572-630, values probe-verified in tests/golden/composite_pins.json
+    int ntsc, line_width, line_count, hsync, hsync_long, hsync_short, burst_start, burst_width, active_start;
+    int active_top, vsync_start, blit_start;      // blit_start = active_start + 16 (+80 PAL)
+};
+
+struct EfDev {               // device-visible context (lives in device memory)
+    int n_streams, max_pictures, max_slices, max_seq;
+    const uint8_t* es;
+    const uint64_t* es_off;
+    uint8_t* frames;
+    EfSeq* seq;              // [n_streams][max_seq + 1]
+    EfPic* pics;             // [n_streams][max_pictures]
+    uint32_t* slice_off;     // [n_streams][max_slices]
+    uint8_t* slice_code;     // [n_streams][max_slices]
+    uint32_t* n_pics;        // [n_streams] pictures in the current submit
+    uint32_t* base_pics;     // [n_streams] pictures decoded before the current submit (ping-pong phase)
+    uint32_t* n_seq;         // [n_streams] sequence headers seen in the current submit
+    uint32_t* pic_pref;      // [max_pictures][n_streams] exclusive prefix of n_slices over streams
+    uint32_t* pic_total;     // [max_pictures] slices of that picture index over all streams
+    uint32_t* pic_base;      // [max_pictures] start of that picture's range in `work`
+    uint32_t* cursor;        // [max_pictures] work-stealing cursor of K1
+    EfWork* work;            // flat, grouped by picture index
+    uint32_t* info;          // [8]: 0 max pictures, 1 total pictures, 2 total slices, 3 error flags
+    const EfTables* tables;
+    uint16_t* fields;        // [n_streams][field_stride]
+    const uint32_t* color_tab;   // [768]
+    const int16_t* pal_burst;    // [2][64]
+    size_t field_stride;     // samples
+    size_t work_capacity;
+    EfGeometry geo;
+};
+
+static inline __host__ __device__ size_t ef_frame_offset(int stream, int fb) { return ((size_t)stream * 2 + (size_t)fb) * EF_FRAME; }

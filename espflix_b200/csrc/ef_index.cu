@@ -1,0 +1,318 @@
+// espflix_b200/csrc/ef_index.cu — K1a: start-code scan, header parse and slice work lists, done
+// once per submit for the whole batch, entirely on the device.
+//
+// Replaces the serial start-code search of MpegDecoder::run() (player.cpp:1360-1363), the marker
+// dispatch (player.cpp:1318-1340) and the header parsers sequence()/gop()/picture()
+// (player.cpp:658-724). The reference walks the stream bit by bit from one start code to the next;
+// start codes are byte aligned in every stream it accepts (Q8), so here a warp sweeps 512 bytes of
+// one stream per step with 128-bit loads, finds "00 00 01 xx" with byte permutes, and orders the
+// hits with a ballot + popcount prefix so the picture/slice tables come out in stream order.
+//   ef_scan_kernel    one warp per stream   -> seq[], pics[], slice_off[], slice_code[], n_pics[]
+//   ef_prefix_kernel  one CTA               -> per picture index: exclusive prefix over streams
+//   ef_fill_kernel    one thread per (picture, stream) -> flat EfWork list per picture index
+// TS input (the reference's wire format) is first compacted to an elementary stream by
+//   ef_ts_len_kernel / ef_ts_copy_kernel    one thread per 188-byte packet (more()/demux(),
+//                                           player.cpp:381-493)
+#include "ef_common.cuh"
+#include "ef_iso11172_tables.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t ld_byte(const uint8_t* es, uint64_t len, uint64_t i) { return i < len ? es[i] : 0u; }
+
+// read `n` (<= 24) bits at bit offset `bit` of the stream
+__device__ __forceinline__ uint32_t bits_at(const uint8_t* es, uint64_t len, uint64_t bit, int n)
+{
+    uint64_t byte = bit >> 3;
+    uint32_t w = (ld_byte(es, len, byte) << 24) | (ld_byte(es, len, byte + 1) << 16) | (ld_byte(es, len, byte + 2) << 8) | ld_byte(es, len, byte + 3);
+    return (w << (bit & 7)) >> (32 - n);
+}
+
+__constant__ uint8_t c_default_intra_q[64];
+
+}  // namespace
+
+cudaError_t ef_index_upload_constants()
+{
+    return cudaMemcpyToSymbol(c_default_intra_q, ef_default_intra_q, 64);
+}
+
+__global__ void __launch_bounds__(128)
+ef_scan_kernel(EfDev* __restrict__ Dp)
+{
+    EfDev& D = *Dp;
+    const int lane = threadIdx.x & 31;
+    const int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (s >= D.n_streams) return;
+
+    EfSeq* seqs = D.seq + (size_t)s * (D.max_seq + 1);
+    EfPic* pics = D.pics + (size_t)s * D.max_pictures;
+    uint32_t* soff = D.slice_off + (size_t)s * D.max_slices;
+    uint8_t* scode = D.slice_code + (size_t)s * D.max_slices;
+
+    // roll the state of the previous submit: ping-pong phase and the last sequence header
+    {
+        const uint32_t prev_seq = min(D.n_seq[s], (uint32_t)D.max_seq);
+        if (prev_seq) {
+            const uint32_t* src = (const uint32_t*)(seqs + prev_seq);
+            uint32_t* dst = (uint32_t*)seqs;
+            for (int i = lane; i < (int)(sizeof(EfSeq) / 4); i += 32) dst[i] = src[i];
+        }
+        if (lane == 0) { D.base_pics[s] += D.n_pics[s]; }
+        __syncwarp();
+    }
+
+    const uint8_t* es = D.es + D.es_off[s];
+    const uint64_t len = D.es_off[s + 1] - D.es_off[s];
+    const uintptr_t misalign = (uintptr_t)es & 15;
+    const uint8_t* abase = es - misalign;                 // 16-byte aligned sweep origin
+    const uint64_t span = len + misalign;
+
+    uint32_t n_pic = 0, n_slice = 0, n_seq = 0;           // warp-uniform running counts
+    uint32_t fp_rs = 0;                                   // full_pel | r_size << 1 of the last P header (stale state a B/D picture would see)
+    bool stop = false;
+
+    for (uint64_t chunk = 0; chunk < span && !stop; chunk += 512) {
+        const uint64_t o = chunk + (uint64_t)lane * 16;
+        uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        uint32_t nxt = 0xFFFFFFFFu;
+        if (o < span) v = __ldg((const uint4*)(abase + o));
+        if (o + 16 < span) nxt = __ldg((const uint32_t*)(abase + o + 16));
+        const uint32_t w[5] = { v.x, v.y, v.z, v.w, nxt };
+        uint32_t hits = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            // little-endian words: bytes i..i+3 of the 20-byte window
+            const uint32_t q = __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], (i & 3) * 8);
+            const int64_t at = (int64_t)(o + i) - (int64_t)misalign;          // stream-relative position of the first zero byte
+            if ((q & 0x00FFFFFFu) == 0x00010000u && at >= 0 && (uint64_t)at + 4 <= len) hits |= 1u << i;
+        }
+        unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
+        while (lanes && !stop) {
+            const int src = __ffs(lanes) - 1;
+            uint32_t h = __shfl_sync(0xFFFFFFFFu, hits, src);
+            const uint64_t obase = chunk + (uint64_t)src * 16;
+            while (h && !stop) {
+                const int i = __ffs(h) - 1;
+                h &= h - 1;
+                const uint64_t pos = obase + i - misalign;                    // first 00 of the start code
+                const uint32_t code = ld_byte(es, len, pos + 3);
+                if (code == 0x00) {                                           // picture(), player.cpp:704
+                    const uint32_t idx = n_pic++;
+                    const uint64_t hb = (pos + 4) * 8;
+                    const uint32_t type = bits_at(es, len, hb + 10, 3);
+                    if (type == 2) {
+                        const uint32_t fp = bits_at(es, len, hb + 29, 1);
+                        const uint32_t fc = bits_at(es, len, hb + 30, 3);
+                        fp_rs = fp | (((fc - 1u) & 7u) << 1);
+                    }
+                    if (idx < (uint32_t)D.max_pictures && lane == 0) {
+                        EfPic p;
+                        p.first_slice = n_slice; p.n_slices = 0; p.type = (uint8_t)type; p.fp_rsize = (uint8_t)fp_rs;
+                        p.seq = (uint16_t)min(n_seq, (uint32_t)D.max_seq); p.pad = 0;
+                        pics[idx] = p;
+                    }
+                } else if (code >= 0x01 && code <= 0xAF) {                    // slice start code
+                    if (n_pic > 0) {
+                        const uint32_t j = n_slice++;
+                        if (j < (uint32_t)D.max_slices && lane == 0) { soff[j] = (uint32_t)(pos + 4); scode[j] = (uint8_t)code; }
+                    }
+                } else if (code == 0xB3) {                                    // sequence(), player.cpp:658
+                    const uint32_t k = ++n_seq;
+                    if (k <= (uint32_t)D.max_seq) {
+                        const uint64_t hb = (pos + 4) * 8;
+                        const uint32_t hsize = bits_at(es, len, hb, 12), vsize = bits_at(es, len, hb + 12, 12);
+                        const uint32_t load_intra = bits_at(es, len, hb + 62, 1);
+                        const uint64_t after_intra = hb + 63 + (load_intra ? 512 : 0);
+                        const uint32_t load_inter = bits_at(es, len, after_intra, 1);
+                        EfSeq* q = seqs + k;
+                        for (int e = lane; e < 64; e += 32) {
+                            // Q4: the decoder keeps the 64 bytes in stream order and indexes them with the raster index
+                            const uint32_t qi = load_intra ? bits_at(es, len, hb + 63 + 8 * e, 8) : c_default_intra_q[e];
+                            const uint32_t qn = load_inter ? bits_at(es, len, after_intra + 1 + 8 * e, 8) : 16u;
+                            const int t = (e & 7) * 8 + (e >> 3);                 // transposed: [col][row]
+                            q->intra_qT[t] = (uint8_t)qi;
+                            q->inter_qT[t] = (uint8_t)qn;
+                        }
+                        if (lane == 0) {
+                            q->mb_width = (uint16_t)((hsize + 15) >> 4);
+                            q->mb_height = (uint16_t)((vsize + 15) >> 4);
+                            q->valid = 1; q->pad0 = 0;
+                        }
+                    }
+                } else if (code == 0xB7) {                                    // sequence end: the reference decoder parks in pause()
+                    stop = true;
+                }
+            }
+            lanes &= lanes - 1;
+        }
+    }
+    __syncwarp();
+
+    // fix-up: slice counts per picture = difference of consecutive first_slice
+    const uint32_t np = min(n_pic, (uint32_t)D.max_pictures);
+    const uint32_t ns = min(n_slice, (uint32_t)D.max_slices);
+    for (uint32_t i = lane; i < np; i += 32) {
+        const uint32_t first = min(pics[i].first_slice, ns);
+        const uint32_t next = i + 1 < np ? min(pics[i + 1].first_slice, ns) : ns;
+        pics[i].n_slices = next - first;
+    }
+    if (lane == 0) {
+        D.n_pics[s] = np;
+        D.n_seq[s] = n_seq;
+        atomicMax(&D.info[0], np);
+        atomicAdd(&D.info[1], np);
+        atomicAdd(&D.info[2], ns);
+        if (n_pic > (uint32_t)D.max_pictures || n_slice > (uint32_t)D.max_slices || n_seq > (uint32_t)D.max_seq) atomicOr(&D.info[3], 1u);
+    }
+}
+
+// exclusive prefix of slices-per-stream for every picture index; single CTA of 1024 threads
+__global__ void __launch_bounds__(1024)
+ef_prefix_kernel(EfDev* __restrict__ Dp)
+{
+    EfDev& D = *Dp;
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry, global_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) global_base = 0;
+    __syncthreads();
+    const int pmax = min((int)D.info[0], D.max_pictures);
+    for (int p = 0; p < D.max_pictures; p++) {
+        if (p >= pmax) {
+            if (threadIdx.x == 0) { D.pic_total[p] = 0; D.pic_base[p] = 0; D.cursor[p] = 0; }
+            continue;
+        }
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base < D.n_streams; base += 1024) {
+            const int s = base + threadIdx.x;
+            uint32_t v = 0;
+            if (s < D.n_streams && (uint32_t)p < D.n_pics[s]) v = D.pics[(size_t)s * D.max_pictures + p].n_slices;
+            uint32_t x = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+            if (lane == 31) warp_sum[warp] = x;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t t = warp_sum[lane], z = t;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
+                warp_sum[lane] = z - t;                   // exclusive offsets of the warps
+            }
+            __syncthreads();
+            const uint32_t excl = carry + warp_sum[warp] + x - v;
+            if (s < D.n_streams) D.pic_pref[(size_t)p * D.n_streams + s] = excl;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = excl + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            D.pic_total[p] = carry;
+            D.pic_base[p] = global_base;
+            D.cursor[p] = 0;
+            global_base += carry;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ef_fill_kernel(EfDev* __restrict__ Dp)
+{
+    EfDev& D = *Dp;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (int)(t / D.n_streams), s = (int)(t % D.n_streams);
+    if (p >= D.max_pictures || (uint32_t)p >= D.n_pics[s]) return;
+    const EfPic pic = D.pics[(size_t)s * D.max_pictures + p];
+    const uint32_t first = pic.first_slice, seq_idx = pic.seq;
+    const size_t dst = (size_t)D.pic_base[p] + D.pic_pref[(size_t)p * D.n_streams + s];
+    // picture types other than I are parsed with the P tables (picture() ignores B/D headers but
+    // their slices still reach slice(), player.cpp:716, 1292)
+    const uint32_t type = pic.type == 1 ? 1u : 2u;
+    for (uint32_t j = 0; j < pic.n_slices; j++) {
+        if (dst + j >= D.work_capacity) { atomicOr(&D.info[3], 2u); return; }
+        EfWork w;
+        w.stream = (uint32_t)s;
+        w.es_off = D.slice_off[(size_t)s * D.max_slices + first + j];
+        w.info = (uint32_t)D.slice_code[(size_t)s * D.max_slices + first + j] | (type << 8) | ((uint32_t)(pic.fp_rsize & 15) << 11) | (seq_idx << 16);
+        w.pad = 0;
+        D.work[dst + j] = w;
+    }
+}
+
+// ---- TS -> ES compaction -------------------------------------------------------------------------
+// One thread per 188-byte packet: payload start/length for PID 0x100 following more()/demux()
+// (player.cpp:381-493): sync byte, adaptation field, PES header skipped on payload_unit_start.
+__device__ __forceinline__ void ts_payload(const uint8_t* d, int& start, int& n)
+{
+    start = 188; n = 0;
+    if (d[0] != 0x47) return;
+    const int pid = ((d[1] << 8) | d[2]) & 0x1FFF;
+    if (pid != 0x100 || !(d[3] & 0x10)) return;
+    int o = 4;
+    if (d[3] & 0x20) o = 5 + d[4];
+    if (d[1] & 0x40) { if (o + 9 > 188) return; o = o + 9 + d[o + 8]; }      // payload = d + 6 + 3 + header_data_length
+    if (o < 188) { start = o; n = 188 - o; }
+}
+
+// pass 1: per-packet payload length -> out_len[pkt]; pass 2 (after a device scan): copy
+__global__ void ef_ts_len_kernel(const uint8_t* __restrict__ ts, uint64_t n_packets, uint32_t* __restrict__ out_len)
+{
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_packets) return;
+    int start, n;
+    ts_payload(ts + k * 188, start, n);
+    out_len[k] = (uint32_t)n;
+}
+
+__global__ void ef_ts_copy_kernel(const uint8_t* __restrict__ ts, uint64_t n_packets, const uint64_t* __restrict__ out_off, uint8_t* __restrict__ es)
+{
+    // one warp per packet: lanes copy the payload bytes
+    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= n_packets) return;
+    const uint8_t* d = ts + k * 188;
+    int start, n;
+    ts_payload(d, start, n);
+    uint8_t* dst = es + out_off[k];
+    for (int i = lane; i < n; i += 32) dst[i] = d[start + i];
+}
+
+// exclusive scan of u32 lengths into u64 offsets, plus per-stream ES offsets: single CTA, sequential over chunks
+__global__ void __launch_bounds__(1024)
+ef_ts_scan_kernel(const uint32_t* __restrict__ len, uint64_t n_packets, uint64_t* __restrict__ off,
+                  const uint64_t* __restrict__ ts_off, int n_streams, uint64_t* __restrict__ es_off)
+{
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n_packets; base += 1024) {
+        const uint64_t k = base + threadIdx.x;
+        const uint64_t v = k < n_packets ? len[k] : 0;
+        uint64_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t t = warp_sum[lane], z = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
+            warp_sum[lane] = z - t;
+        }
+        __syncthreads();
+        const uint64_t excl = carry + warp_sum[warp] + x - v;
+        if (k < n_packets) off[k] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    // stream boundaries: ES offset of stream s = offset of its first packet
+    for (int s = threadIdx.x; s <= n_streams; s += 1024) {
+        const uint64_t pk = ts_off[s] / 188;
+        es_off[s] = pk < n_packets ? off[pk] : carry;
+    }
+}

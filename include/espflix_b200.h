@@ -1,0 +1,127 @@
+/* include/espflix_b200.h — C-ABI of libespflix_b200.so: the B200 drop-in for the espflix hot path
+ * (MPEG-1 decode of a batch of independent 352x192 streams + NTSC/PAL composite synthesis).
+ *
+ * Plain C, plain pointers and sizes, no exceptions, no torch types. Every function returns
+ * EF_OK (0) or a negative EF_E* code; ef_last_error() gives a text for the last failure on
+ * the calling thread. A context owns all device memory for one GPU; calls on one context are
+ * single-threaded (like the reference's one decoder thread, espflix.cpp:657). There is NO CPU
+ * fallback: every entry point fails with EF_ECUDA if the CUDA device is missing.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference/src):
+ *
+ *   ef_create / ef_destroy        MpegDecoder::MpegDecoder(Frame*,Frame*) player.cpp:354 and the
+ *                                 two Frame::init() calls (player.cpp:25) of espflix.cpp:651 -
+ *                                 here for n_streams independent decoders at once
+ *   ef_reset                      MpegDecoder::reset() player.cpp:439 (+ video_reset video.cpp:1076)
+ *   ef_submit_es / ef_submit_ts   MpegDecoder::push_full(Buffer*) player.cpp:371 — the producer side
+ *                                 of the Buffer queue (streamer.h:139); _ts takes the reference's wire
+ *                                 format (188-byte TS, PID 0x100; demux of player.cpp:381-493), _es
+ *                                 takes the video elementary stream the demux yields
+ *   ef_index                      the start-code search of MpegDecoder::run() player.cpp:1360-1363 and
+ *                                 the marker dispatch player.cpp:1318 for sequence/gop/picture headers
+ *                                 (player.cpp:658-724), done once per submit for the whole batch
+ *   ef_decode_picture             MpegDecoder::slice() player.cpp:1251 and everything under it
+ *                                 (block/idct/mocomp/predict/copy_block..., player.cpp:733-1236) for
+ *                                 picture #pic of every stream: ONE fused kernel launch
+ *   ef_decode_all                 the for(;;) of MpegDecoder::run() player.cpp:1355 over one submit
+ *   ef_read_frame / _i420         what push_video(Frame*,front,pts,mode) video.h:49 hands to the
+ *                                 display side: the striped Frame (video.h:36-44) of one stream
+ *   ef_video_init                 video_init(int ntsc) video.cpp:572
+ *   ef_composite_field            one field's worth of video_isr() calls video.cpp:1122 (sync, burst,
+ *                                 blit video.cpp:690, blanking, vsync) for every stream: ONE launch
+ *   ef_read_field / ef_video_isr  the uint16 line buffer video_isr(volatile void*) fills
+ *   ef_blit                       blit(Frame*,uint16_t*,line,x,width) video.cpp:690
+ */
+#ifndef ESPFLIX_B200_H
+#define ESPFLIX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EF_OK        0
+#define EF_EINVAL   (-1)   /* bad argument */
+#define EF_ECUDA    (-2)   /* CUDA runtime error / no device (no CPU fallback exists) */
+#define EF_ENOMEM   (-3)   /* a capacity given to ef_create was exceeded */
+#define EF_ESTATE   (-4)   /* call out of order (e.g. decode before index) */
+
+#define EF_FB_WIDTH    352           /* video.h:30 */
+#define EF_FB_HEIGHT   192
+#define EF_FB_STRIDE   528           /* video.h:32: 352 luma + 176 chroma per strip row */
+#define EF_FB_STRIPS   12
+#define EF_STRIP_BYTES 8448          /* 16 rows x 528 */
+#define EF_FRAME_BYTES 101376        /* 12 strips, contiguous on the device */
+#define EF_I420_BYTES  101376
+#define EF_NTSC_FIELD_SAMPLES (262 * 912)
+#define EF_PAL_FIELD_SAMPLES  (312 * 1136)
+
+typedef struct ef_ctx ef_ctx;
+
+typedef struct {
+    int device;                 /* CUDA device ordinal */
+    int n_streams;              /* independent decoders in this context */
+    int max_pictures;           /* per stream per submit */
+    int max_slices_per_picture; /* per stream (reference accepts slice codes 1..12) */
+    size_t es_capacity;         /* bytes of elementary stream per submit, whole batch */
+    int fields;                 /* 1: allocate composite field buffers (n_streams x PAL field) */
+} ef_config;
+
+const char* ef_last_error(void);
+const char* ef_version(void);
+
+int ef_create(ef_ctx** out, const ef_config* cfg);
+void ef_destroy(ef_ctx* ctx);
+int ef_reset(ef_ctx* ctx);      /* zero frame stores, picture counters and sequence state */
+
+/* Submit one batch. es/ts = all streams back to back; off[n_streams+1] = byte offsets of each
+ * stream in it. The *_host forms copy from (pinned or pageable) host memory; *_device forms take
+ * device pointers (inputs already resident in HBM). `stream` is a cudaStream_t (0 = default).
+ * Each submit must hold whole pictures (cut at picture/sequence start codes). */
+int ef_submit_es_host(ef_ctx* ctx, const uint8_t* es, const uint64_t* off, void* stream);
+int ef_submit_es_device(ef_ctx* ctx, const uint8_t* es, const uint64_t* off, void* stream);
+int ef_submit_ts_host(ef_ctx* ctx, const uint8_t* ts, const uint64_t* off, void* stream);
+int ef_submit_ts_device(ef_ctx* ctx, const uint8_t* ts, const uint64_t* off, void* stream);
+
+/* K1a: start-code scan, header parse, per-picture slice work lists (device side, asynchronous). */
+int ef_index(ef_ctx* ctx, void* stream);
+/* Synchronising query of the last ef_index: max pictures in any stream, total pictures, total slices. */
+int ef_index_info(ef_ctx* ctx, int* max_pictures, uint64_t* total_pictures, uint64_t* total_slices, uint64_t* es_bytes);
+/* Per-stream picture count of the last submit and pictures decoded before it (host arrays, may be NULL). */
+int ef_stream_info(ef_ctx* ctx, int stream_index, int* n_pictures, int* base_pictures);
+
+/* K1: decode picture #pic (0-based within the submit) of every stream — one launch. */
+int ef_decode_picture(ef_ctx* ctx, int pic, void* stream);
+/* All pictures 0..n_pictures-1 of the submit, back to back on `stream`. */
+int ef_decode_all(ef_ctx* ctx, int n_pictures, void* stream);
+
+/* Frame stores. fb = 0/1 is the reference's _fb[] index; -1 = the frame holding the most recently
+ * decoded picture of that stream (what the next push_video would present). Synchronous. */
+int ef_read_frame(ef_ctx* ctx, int stream_index, int fb, uint8_t* dst_strips /* EF_FRAME_BYTES */);
+int ef_read_frame_i420(ef_ctx* ctx, int stream_index, int fb, uint8_t* dst /* EF_I420_BYTES */);
+int ef_write_frame_i420(ef_ctx* ctx, int stream_index, int fb, const uint8_t* src);   /* tests / GUI-drawn frames */
+/* Device address of a stream's frame store (for zero-copy consumers); fb as above but not -1. */
+int ef_frame_device_ptr(ef_ctx* ctx, int stream_index, int fb, void** ptr);
+/* Batched read-back of the most recent picture of streams [first, first+count) as I420. */
+int ef_read_latest_i420(ef_ctx* ctx, int first, int count, uint8_t* dst, void* stream);
+
+/* K2: composite synthesis. */
+int ef_video_init(ef_ctx* ctx, int ntsc);                          /* 1 NTSC, 0 PAL */
+int ef_video_geometry(ef_ctx* ctx, int* line_width, int* line_count);
+/* One field for every stream from frame `fb` (-1 = most recent picture), `frame_counter` = the
+ * reference's _frame_counter (dither phase), one launch. */
+int ef_composite_field(ef_ctx* ctx, int fb, int frame_counter, void* stream);
+int ef_read_field(ef_ctx* ctx, int stream_index, uint16_t* dst /* line_count*line_width */);
+/* video_isr-style single line fetch from the last synthesised field of stream_index. */
+int ef_video_isr(ef_ctx* ctx, int stream_index, int line, uint16_t* buf /* line_width */);
+/* blit(): width luma pixels starting at x of line (0..191) -> 2*width samples at dst (host). */
+int ef_blit(ef_ctx* ctx, int stream_index, int fb, uint16_t* dst, int line, int x, int width, int frame_counter);
+
+/* Launch counter: kernels this library has launched since ef_create (bench.py "gpu_launches"). */
+uint64_t ef_launch_count(ef_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

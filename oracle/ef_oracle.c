@@ -59,6 +59,11 @@ static void tables_init(void)
     tables_ready = 1;
 }
 
+/* coverage counters (test assertions only): which decoder paths an input exercised */
+static efo_stats g_stats;
+void efo_stats_reset(void) { memset(&g_stats, 0, sizeof(g_stats)); }
+void efo_stats_get(efo_stats* s) { *s = g_stats; }
+
 /* ------------------------------------------------------------------------------------------
  * TS demux — MpegDecoder::more / demux / parse_pts (player.cpp:294-307, 381-436, 459-493)
  * ---------------------------------------------------------------------------------------- */
@@ -184,7 +189,11 @@ void efo_strips_to_i420(const uint8_t* f, uint8_t* d)
     for (int y = 0; y < 96; y++, d += 176) memcpy(d, get_cb((uint8_t*)f, y), 176);
 }
 
-static int pin(int x) { return x < 0 ? 0 : x > 248 ? 248 : x; }   /* _pin LUT, player.cpp:183-236 (Q1) */
+static int pin(int x)   /* _pin LUT, player.cpp:183-236 (Q1); the table covers -256..511, outside is undefined in the reference */
+{
+    if (x < -256 || x > 511) g_stats.pin_out_of_domain++;
+    return x < 0 ? 0 : x > 248 ? 248 : x;
+}
 
 /* ------------------------------------------------------------------------------------------
  * headers — sequence/gop/picture/flush_picture (player.cpp:646-724)
@@ -225,11 +234,13 @@ static void picture(dec_t* d)                          /* player.cpp:704 */
     flush_picture(d, 0);
     get_bits(d, 10);
     d->picture_coding_type = (int)get_bits(d, 3);
+    g_stats.pictures[d->picture_coding_type & 7]++;
     if (d->picture_coding_type != 1 && d->picture_coding_type != 2) return;
     get_bits(d, 16);
     if (d->picture_coding_type == 2) {
         d->full_pel_forward = get_bit(d);
         d->forward_r_size = (int)get_bits(d, 3) - 1;
+        g_stats.f_code[(d->forward_r_size + 1) & 7]++;
     }
 }
 
@@ -248,6 +259,7 @@ static const uint8_t* ref_row(dec_t* d, int c, int y)
 static void mocomp(dec_t* d, uint8_t* dst, int pos_x, int pos_y, int size, int c)   /* player.cpp:733 */
 {
     int xh = pos_x & 1, yh = pos_y & 1;
+    if (size == 16) g_stats.mocomp_xy[(yh << 1) | xh]++;
     pos_y >>= 1; pos_x >>= 1;
     dst += size * d->mb_x;
     for (int y = 0; y < size; y++) {
@@ -382,6 +394,8 @@ static int block(dec_t* d, int blk, int intra)
             if (v == 0) {                              /* escape (player.cpp:1092-1099) */
                 run = (int)get_bits(d, 6);
                 v = (int)get_bits(d, 8);
+                g_stats.escapes++;
+                if (v == 0 || v == 128) g_stats.escapes16++;
                 if (v == 0) v = (int)get_bits(d, 8);
                 else if (v == 128) v = (int)get_bits(d, 8) - 256;
                 else if (v > 128) v -= 256;
@@ -393,7 +407,9 @@ static int block(dec_t* d, int blk, int intra)
         v <<= 1;
         if (!intra) v += v < 0 ? -1 : 1;
         v = (v * d->quantizer_scale * q[zz]) / 16;
+        if (v == 0) g_stats.q2_zero++;
         if ((v & 1) == 0) v -= v > 0 ? 1 : -1;         /* Q2 */
+        if (v > 2047 || v < -2048) g_stats.saturated++;
         if (v > 2047) v = 2047; else if (v < -2048) v = -2048;
         b[zz] = v * ef_aan_prescale[zz];
     }
@@ -407,8 +423,10 @@ static int block(dec_t* d, int blk, int intra)
         case 5: dst = d->cb_addr + (d->mb_x << 3); break;
     }
 
+    g_stats.blocks++;
     if (n == 1) {                                      /* Q5: DC-only blocks bypass the IDCT */
         int dc = b[0] >> 8;
+        g_stats.blocks_dc_only++;
         if (intra) {                                   /* copy_block_dc: no clamp (Q7) */
             uint32_t w = (uint32_t)dc; w |= w << 8; w |= w << 16;
             for (int i = 0; i < 8; i++, dst += 528) { memcpy(dst, &w, 4); memcpy(dst + 4, &w, 4); }
@@ -449,6 +467,7 @@ static int slice(dec_t* d, int s)
     reset_predictors(d);
     d->quantizer_scale = (int)get_bits(d, 5);
     while (get_bit(d)) get_bits(d, 8);
+    g_stats.slices++;
 
     for (int mb = 0; peek_bits(d, 23) != 0; mb++) {    /* slice_done (player.cpp:1238) */
         int increment = 0;
@@ -463,6 +482,7 @@ static int slice(dec_t* d, int s)
             while (increment > 1) {
                 inc_mb(d);
                 if (d->mb_y >= d->mb_height) return -1;   /* reference: out-of-bounds write */
+                g_stats.skipped++;
                 predict_zero(d);
                 increment--;
             }
@@ -472,6 +492,8 @@ static int slice(dec_t* d, int s)
 
         int mb_type = get_vlc(d, d->picture_coding_type == 1 ? &T_type_i : &T_type_p);
         int intra = mb_type & 0x01;
+        g_stats.mb_type[mb_type & 31]++;
+        if (d->picture_coding_type == 2 && d->full_pel_forward) g_stats.full_pel_mbs++;
         if (mb_type & 0x10) d->quantizer_scale = (int)get_bits(d, 5);
         if (intra) d->forward_motion_h = d->forward_motion_v = 0;
         else {

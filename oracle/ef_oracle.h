@@ -39,6 +39,18 @@ size_t efo_demux_ts(const uint8_t* ts, size_t len, uint8_t* es, size_t es_cap,
 long efo_decode_es(const uint8_t* es, size_t len, int has_pts,
                    uint8_t* out_i420, size_t cap_frames, uint8_t* strips_out);
 
+/* Coverage counters accumulated by efo_decode_es since the last reset (process-global; tests only). */
+typedef struct {
+    uint64_t pictures[8];      /* by picture_coding_type */
+    uint64_t f_code[8];        /* forward_f_code histogram over P pictures */
+    uint64_t slices, skipped, blocks, blocks_dc_only, escapes, escapes16, saturated, q2_zero, full_pel_mbs;
+    uint64_t mb_type[32];      /* by macroblock_type flags (0x10 quant | 0x08 fwd | 0x02 pattern | 0x01 intra) */
+    uint64_t mocomp_xy[4];     /* luma mocomp cases (yhalf<<1 | xhalf), non-zero vectors only */
+    uint64_t pin_out_of_domain; /* clamp inputs outside [-256,511]: the reference reads out of bounds there (UB) */
+} efo_stats;
+void efo_stats_reset(void);
+void efo_stats_get(efo_stats* s);
+
 /* TS convenience wrapper = efo_demux_ts + efo_decode_es (has_pts from the PES headers). */
 long efo_decode_ts(const uint8_t* ts, size_t len, uint8_t* out_i420, size_t cap_frames);
 

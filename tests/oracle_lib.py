@@ -1,0 +1,164 @@
+"""tests/oracle_lib.py — loads the CPU checkers under oracle/ (TEST INFRASTRUCTURE). Only tests,
+__graft_entry__.smoke() and bench.py's cpu_baseline/reference legs import this."""
+import ctypes
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+I420 = 101376
+FRAME = 101376
+REF_DECODE = os.path.join(ROOT, "oracle", "_ref", "efref_decode")
+REF_VIDEO = os.path.join(ROOT, "oracle", "_ref", "libefref_vid.so")
+
+
+class _Video(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in "ntsc line_width line_count hsync hsync_long hsync_short burst_start burst_width active_start".split()] + \
+               [("color_tab", ctypes.c_uint32 * 768), ("burst0", ctypes.c_int16 * 64), ("burst1", ctypes.c_int16 * 64)]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [("pictures", ctypes.c_uint64 * 8), ("f_code", ctypes.c_uint64 * 8)] + \
+               [(n, ctypes.c_uint64) for n in "slices skipped blocks blocks_dc_only escapes escapes16 saturated q2_zero full_pel_mbs".split()] + \
+               [("mb_type", ctypes.c_uint64 * 32), ("mocomp_xy", ctypes.c_uint64 * 4), ("pin_out_of_domain", ctypes.c_uint64)]
+
+
+class Oracle:
+    """The C restatement (oracle/libef_oracle.so)."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "libef_oracle.so"))
+        L, VP = self.lib, ctypes.c_void_p
+        L.efo_demux_ts.restype = ctypes.c_size_t
+        L.efo_demux_ts.argtypes = [VP, ctypes.c_size_t, VP, ctypes.c_size_t, VP, VP, ctypes.c_size_t, VP]
+        L.efo_decode_es.restype = ctypes.c_long
+        L.efo_decode_es.argtypes = [VP, ctypes.c_size_t, ctypes.c_int, VP, ctypes.c_size_t, VP]
+        L.efo_decode_ts.restype = ctypes.c_long
+        L.efo_decode_ts.argtypes = [VP, ctypes.c_size_t, VP, ctypes.c_size_t]
+        L.efo_idct.argtypes = [VP]
+        L.efo_i420_to_strips.argtypes = [VP, VP]
+        L.efo_strips_to_i420.argtypes = [VP, VP]
+        L.efo_video_init.argtypes = [VP, ctypes.c_int]
+        L.efo_blit.argtypes = [VP, VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.efo_field.argtypes = [VP, VP, ctypes.c_int, VP]
+        L.efo_stats_get.argtypes = [VP]
+        self._video = {}
+
+    def demux_ts(self, ts):
+        ts = np.ascontiguousarray(np.frombuffer(bytes(ts), dtype=np.uint8))
+        es = np.empty(ts.size + 16, dtype=np.uint8)
+        n = self.lib.efo_demux_ts(ts.ctypes.data, ts.size, es.ctypes.data, es.size, None, None, 0, None)
+        return es[:n].copy()
+
+    def decode_es(self, es, has_pts=True, max_frames=256):
+        es = np.ascontiguousarray(np.frombuffer(bytes(es), dtype=np.uint8))
+        out = np.zeros((max_frames, I420), dtype=np.uint8)
+        n = self.lib.efo_decode_es(es.ctypes.data, es.size, 1 if has_pts else 0, out.ctypes.data, max_frames, None)
+        assert n <= max_frames
+        return out[:n]
+
+    def decode_ts(self, ts, max_frames=256):
+        ts = np.ascontiguousarray(np.frombuffer(bytes(ts), dtype=np.uint8))
+        out = np.zeros((max_frames, I420), dtype=np.uint8)
+        n = self.lib.efo_decode_ts(ts.ctypes.data, ts.size, out.ctypes.data, max_frames)
+        assert n <= max_frames
+        return out[:n]
+
+    def idct(self, coeffs):
+        b = np.ascontiguousarray(coeffs, dtype=np.int32).copy()
+        self.lib.efo_idct(b.ctypes.data)
+        return b
+
+    def i420_to_strips(self, i420):
+        i420 = np.ascontiguousarray(i420, dtype=np.uint8)
+        out = np.zeros(FRAME, dtype=np.uint8)
+        self.lib.efo_i420_to_strips(i420.ctypes.data, out.ctypes.data)
+        return out
+
+    def strips_to_i420(self, strips):
+        strips = np.ascontiguousarray(strips, dtype=np.uint8)
+        out = np.zeros(I420, dtype=np.uint8)
+        self.lib.efo_strips_to_i420(strips.ctypes.data, out.ctypes.data)
+        return out
+
+    def video(self, ntsc):
+        if ntsc not in self._video:
+            v = _Video()
+            self.lib.efo_video_init(ctypes.byref(v), 1 if ntsc else 0)
+            self._video[ntsc] = v
+        return self._video[ntsc]
+
+    def field(self, i420, ntsc, frame_counter):
+        v = self.video(ntsc)
+        strips = self.i420_to_strips(i420)
+        out = np.zeros(v.line_width * v.line_count, dtype=np.uint16)
+        self.lib.efo_field(ctypes.byref(v), strips.ctypes.data, frame_counter, out.ctypes.data)
+        return out
+
+    def blit(self, i420, ntsc, line, x, width, frame_counter):
+        v = self.video(ntsc)
+        strips = self.i420_to_strips(i420)
+        out = np.zeros(2 * 352 + 160, dtype=np.uint16)
+        self.lib.efo_blit(ctypes.byref(v), strips.ctypes.data, out.ctypes.data, line, x, width, frame_counter)
+        return out
+
+    def stats_reset(self):
+        self.lib.efo_stats_reset()
+
+    def stats(self):
+        s = _Stats()
+        self.lib.efo_stats_get(ctypes.byref(s))
+        return s
+
+
+def have_ref():
+    return os.path.exists(REF_DECODE) and os.path.exists(REF_VIDEO)
+
+
+def ref_decode_ts(ts, loops=1, dump=True, timeout=300):
+    """Run the UNMODIFIED reference decoder (oracle/_ref/efref_decode, one process per call, Q11)."""
+    with tempfile.TemporaryDirectory() as d:
+        tin, tout = os.path.join(d, "in.ts"), os.path.join(d, "out.i420")
+        with open(tin, "wb") as f:
+            f.write(bytes(ts))
+        r = subprocess.run([REF_DECODE, tin, tout if dump else "-", str(loops)], capture_output=True, timeout=timeout, check=True)
+        info = json.loads(r.stdout)
+        frames = np.fromfile(tout, dtype=np.uint8).reshape(-1, I420) if dump else None
+        return info, frames
+
+
+class RefVideo:
+    """The UNMODIFIED reference composite code (oracle/_ref/libefref_vid.so)."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(REF_VIDEO)
+        VP = ctypes.c_void_p
+        self.lib.efref_field.restype = ctypes.c_long
+        self.lib.efref_field.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int, VP]
+        self.lib.efref_blit.argtypes = [VP, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        self.std = None
+
+    def init(self, ntsc):
+        if self.std != ntsc:
+            self.lib.efref_video_init(1 if ntsc else 0)
+            self.std = ntsc
+        g = (ctypes.c_int * 8)()
+        self.lib.efref_geometry(g)
+        return list(g)
+
+    def field(self, i420, ntsc, frame_counter):
+        g = self.init(ntsc)
+        i420 = np.ascontiguousarray(i420, dtype=np.uint8)
+        out = np.zeros(g[0] * g[1], dtype=np.uint16)
+        self.lib.efref_field(i420.ctypes.data, None, frame_counter, 0, out.ctypes.data)
+        return out
+
+    def blit(self, i420, ntsc, line, x, width, frame_counter):
+        self.init(ntsc)
+        i420 = np.ascontiguousarray(i420, dtype=np.uint8)
+        out = np.zeros(2 * 352 + 160, dtype=np.uint16)
+        self.lib.efref_blit(i420.ctypes.data, frame_counter, out.ctypes.data, line, x, width)
+        return out
