@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py — BASELINE.json metric: 352x192 MPEG-1 frames/sec/GPU (decoded YUV bit-exact vs reference).
+
+Workload (BASELINE.json configs[3], SURVEY.md 8d "Config 4"): 4,096 independent synthetic streams
+per GPU, each one GOP of 12 pictures (1 I + 11 P, 12 slices/picture, ~7.4 KB/picture), D=64 distinct
+seeds replicated 64x (replication only bounds generation time; parity of the distinct streams is
+checked in tests/). A step = one pass of the hot path over the batch: K1a index + 12 launches of the
+fused macroblock kernel K1 = 49,152 decoded pictures per GPU.
+
+  value   whole-job frames/s with the elementary streams already resident in HBM (CUDA events, max over ranks)
+  e2e     same metric through the C-ABI with HOST buffers: pinned ES -> H2D -> index -> decode -> D2H of the
+          last picture of every stream, all inside the timed region
+  roofline  K1: algorithmic bytes (ES + frame written + reference frame read) / summed K1 launch time
+  cpu_baseline / --impl reference   the UNMODIFIED reference decoder (oracle/_ref/efref_decode, one process per
+          core, Q11) on the box's host cores; falls back to the C restatement (kind "port") if _ref is absent
+Multi-GPU: independent streams shard one batch per rank (weak scaling), no data-path collective; one
+all_gather of per-rank frame counts for the report.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "352x192 MPEG-1 frames/sec (decoded YUV bit-exact vs reference)"
+UNIT = "frames/s"
+STREAMS_PER_GPU = 4096
+DISTINCT = 64
+PICTURES = 12
+FRAME_BYTES = 101376
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def workload_config(n_gpus, streams):
+    return {
+        "workload": "config4: %d independent 352x192 streams per GPU x 1 GOP (1 I + 11 P, 12 slices/picture), "
+                    "%d distinct seeds replicated" % (streams, min(DISTINCT, streams)),
+        "streams_per_gpu": streams, "pictures_per_stream": PICTURES, "slices_per_picture": 12,
+        "parallelism": "independent-stream sharding x%d" % n_gpus,
+        "l2": "inputs exceed L2 (ES + frame stores > 126 MB per GPU), no explicit flush",
+    }
+
+
+def make_streams(streams):
+    from espflix_b200 import synth
+    d = min(DISTINCT, streams)
+    gen = synth.generate_many(d, n_pictures=PICTURES, gop=PICTURES, slices=12)
+    return gen, [gen[i % d][0] for i in range(streams)]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(float(r[0])) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own decoder on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_decode_sample(gen, cores, loops):
+    """Every core decodes one distinct stream `loops` times back to back (one process per core: the
+    reference keeps decoder scratch in process globals, Q11). Returns (frames, seconds, kind)."""
+    from espflix_b200 import synth
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "efref_decode")
+    tmp = tempfile.mkdtemp(prefix="efbench_")
+    paths = []
+    for i in range(min(cores, len(gen))):
+        p = os.path.join(tmp, "s%d.ts" % i)
+        with open(p, "wb") as f:
+            f.write(synth.wrap_ts(*gen[i]).tobytes())
+        paths.append(p)
+    if os.path.exists(ref_bin):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([ref_bin, paths[c % len(paths)], "-", str(loops)], stdout=subprocess.PIPE) for c in range(cores)]
+        frames = 0
+        for p in procs:
+            out, _ = p.communicate(timeout=600)
+            frames += json.loads(out)["frames"]
+        return frames, time.perf_counter() - t0, "reference"
+    # fallback: the C restatement, one thread per core (it has no global state)
+    from concurrent.futures import ThreadPoolExecutor
+    from tests.oracle_lib import Oracle
+    o = Oracle()
+    data = [synth.wrap_ts(*gen[i]).tobytes() * max(1, loops // 8) for i in range(min(cores, len(gen)))]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        frames = sum(ex.map(lambda c: int(o.decode_ts(data[c % len(data)], max_frames=PICTURES * max(1, loops // 8) + 2).shape[0]), range(cores)))
+    return frames, time.perf_counter() - t0, "port"
+
+
+def calibrate_loops(gen, target_s):
+    frames, secs, _ = cpu_decode_sample(gen, 1, 20)
+    per_loop = secs / 20.0
+    return max(10, int(target_s / max(per_loop, 1e-6)))
+
+
+def run_reference(args):
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    if rank != 0:
+        return 0
+    gen, _ = make_streams(DISTINCT)
+    cores = os.cpu_count() or 1
+    total_budget = 120.0
+    per_step = min(20.0, total_budget / max(1, args.steps + args.warmup))
+    loops = calibrate_loops(gen, per_step)
+    for _ in range(args.warmup):
+        cpu_decode_sample(gen, cores, max(10, loops // 4))
+    frames = secs = 0.0
+    kind = "reference"
+    for _ in range(args.steps):
+        f, s, kind = cpu_decode_sample(gen, cores, loops)
+        frames += f
+        secs += s
+    value = frames / secs
+    sample = "%d processes x %d loops of one 12-picture synthetic stream each (TS-wrapped, same seeds as the GPU arm)" % (cores, loops)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32/u8", "data": "synthetic", "config": workload_config(args.gpus, STREAMS_PER_GPU),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import espflix_b200
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.gpus > 1 and world == 1:       # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    streams = args.streams
+    gen, stream_list = make_streams(streams)
+    sizes = np.diff(gen[0][1].astype(np.int64))
+    ctx = espflix_b200.Context(n_streams=streams, max_pictures=PICTURES, max_slices_per_picture=12,
+                               es_capacity=sum(len(s) for s in stream_list) + 4096, device=local, fields=False)
+    blob_np, off_np = ctx.pack(stream_list)
+    es_bytes = int(off_np[-1])
+    pinned_es = torch.empty(es_bytes, dtype=torch.uint8, pin_memory=True)
+    pinned_es.numpy()[:] = blob_np
+    pinned_out = torch.empty((streams, FRAME_BYTES), dtype=torch.uint8, pin_memory=True)
+    dev_es = pinned_es.cuda()
+    dev_off = torch.from_numpy(off_np.astype(np.int64)).cuda()
+    st = 0                                                # legacy default stream == torch's default stream
+
+    # algorithmic bytes of K1 per step: I: S + 101,376 ; P: S + 202,752
+    n_i = 1
+    algo_bytes = es_bytes + streams * (n_i * FRAME_BYTES + (PICTURES - n_i) * 2 * FRAME_BYTES)
+
+    def step_resident(events=None):
+        ctx.index(st)
+        if events is not None:
+            events[0].record()
+        for p in range(PICTURES):
+            ctx.decode_picture(p, st)
+            if events is not None:
+                events[p + 1].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.submit_es(dev_es.data_ptr(), dev_off.data_ptr(), st, device=True)
+    for _ in range(args.warmup):
+        step_resident()
+    info = ctx.index_info()
+    assert info["total_pictures"] == streams * PICTURES, info
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(PICTURES + 1)] for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count()
+    barrier()
+    t0.record()
+    for k in range(args.steps):
+        step_resident(ev[k])
+    t1.record()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    ms_total = t0.elapsed_time(t1)
+    k1_ms = sum(ev[k][p].elapsed_time(ev[k][p + 1]) for k in range(args.steps) for p in range(PICTURES))
+
+    # e2e: host buffers through the C-ABI, copies inside the timed region
+    def step_e2e():
+        ctx.submit_es(pinned_es.data_ptr(), off_np, st, device=False)
+        ctx.index(st)
+        ctx.decode_all(PICTURES, st)
+        ctx.read_latest_i420(0, streams, pinned_out.data_ptr(), st)
+
+    step_e2e()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - w0))   # host-blocking copies: take the larger of device and wall time
+    clocks = sampler.summary() if rank == 0 else None
+
+    # max over ranks, total frames via one all_gather (reporting only)
+    frames_done = streams * PICTURES * args.steps
+    if dist is not None:
+        t = torch.tensor([ms_total, k1_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, k1_ms, e2e_ms = [float(x) for x in t.tolist()]
+        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([frames_done], dtype=torch.int64, device="cuda"))
+        total_frames = int(sum(int(c.item()) for c in counts))
+    else:
+        total_frames = frames_done
+    value = total_frames / (ms_total / 1000.0)
+    e2e_value = total_frames / (e2e_ms / 1000.0)
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = algo_bytes * args.steps / (k1_ms / 1000.0) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/u8", "data": "synthetic", "config": workload_config(world, streams),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": es_bytes + int(off_np.nbytes),
+                    "d2h_bytes_per_step": streams * FRAME_BYTES, "ms_per_step": e2e_ms / args.steps,
+                    "what": "pinned ES -> ef_submit_es_host -> ef_index -> 12x ef_decode_picture -> D2H last picture of every stream"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "ef_decode_kernel (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": algo_bytes, "k1_ms_per_step": k1_ms / args.steps,
+                         "k1_share_of_step": k1_ms / ms_total},
+            "per_gpu_frames_per_s": value / world,
+            "es_bytes_per_picture": es_bytes / (streams * PICTURES),
+            "picture_bytes_first_stream": [int(x) for x in sizes],
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            loops = calibrate_loops(gen, 12.0)
+            f, s, kind = cpu_decode_sample(gen, cores, loops)
+            line["cpu_baseline"] = {"value": f / s, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "%d processes x %d loops of one 12-picture synthetic stream each (TS-wrapped), %.1f s" % (cores, loops, s)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    import __graft_entry__
+    if not os.path.exists(os.path.join(ROOT, "espflix_b200", "libespflix_b200.so")):
+        __graft_entry__.build()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

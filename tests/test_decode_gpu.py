@@ -1,0 +1,151 @@
+"""Parity of the CUDA decode path (through the C-ABI) against the oracle and the committed pins.
+Bit-exact: the whole path is integer (the IDCT used is the reference's integer AAN transform)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import espflix_b200
+from espflix_b200 import synth
+from tests.synth_cases import COVERAGE, UNPINNED, make
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def _first_diff(a, b):
+    d = np.nonzero(a != b)[0]
+    return "no diff" if d.size == 0 else "%d bytes differ, first at %d (got %d want %d)" % (d.size, d[0], a[d[0]], b[d[0]])
+
+
+@pytest.mark.parametrize("name", ["splash", "vmedia"])
+def test_reference_fixture_es_path(oracle, name):
+    """config 2: the reference's own embedded streams, every picture byte-exact vs the pins."""
+    pins = json.load(open(os.path.join(G, "decode_pins.json")))[name]
+    es = oracle.demux_ts(open(os.path.join(G, name + ".ts"), "rb").read())
+    ctx = espflix_b200.Context(n_streams=1, max_pictures=128, max_slices_per_picture=8, es_capacity=1 << 20)
+    frames = ctx.decode_sequence([es])[0]
+    assert len(frames) == pins["frames"]
+    for k, f in enumerate(frames):
+        assert hashlib.sha256(f.tobytes()).hexdigest() == pins["frame_sha256"][k], "picture %d" % k
+    assert hashlib.sha256(np.concatenate(frames).tobytes()).hexdigest() == pins["i420_sha256"]
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["splash", "vmedia"])
+def test_reference_fixture_ts_path(oracle, name):
+    """next-row f1: the reference's wire format (188-byte TS, PID 0x100) demuxed on the device."""
+    pins = json.load(open(os.path.join(G, "decode_pins.json")))[name]
+    ts = open(os.path.join(G, name + ".ts"), "rb").read()
+    ctx = espflix_b200.Context(n_streams=1, max_pictures=128, max_slices_per_picture=8, es_capacity=1 << 20)
+    frames = ctx.decode_sequence([ts], ts=True)[0]
+    assert len(frames) == pins["frames"]
+    assert hashlib.sha256(np.concatenate(frames).tobytes()).hexdigest() == pins["i420_sha256"]
+    ctx.close()
+
+
+@pytest.mark.parametrize("idx", range(len(COVERAGE)), ids=[c[0] for c in COVERAGE])
+def test_synthetic_coverage(oracle, idx):
+    name, kw = COVERAGE[idx]
+    es, _ = make(idx, kw)
+    want = oracle.decode_es(es)
+    ctx = espflix_b200.Context(n_streams=1, max_pictures=kw["n_pictures"], es_capacity=1 << 21)
+    frames = ctx.decode_sequence([es])[0]
+    assert len(frames) == want.shape[0] == kw["n_pictures"]
+    for k in range(len(frames)):
+        assert np.array_equal(frames[k], want[k]), "%s picture %d: %s" % (name, k, _first_diff(frames[k], want[k]))
+    ctx.close()
+
+
+@pytest.mark.parametrize("idx", range(len(UNPINNED)), ids=[c[0] for c in UNPINNED])
+def test_outside_reference_domain_matches_oracle(oracle, idx):
+    name, kw = UNPINNED[idx]
+    es, _ = synth.generate(synth.SEED0 + 2000 + idx, **kw)
+    want = oracle.decode_es(es)
+    ctx = espflix_b200.Context(n_streams=1, max_pictures=kw["n_pictures"], es_capacity=1 << 22)
+    frames = ctx.decode_sequence([es])[0]
+    for k in range(len(frames)):
+        assert np.array_equal(frames[k], want[k]), "%s picture %d: %s" % (name, k, _first_diff(frames[k], want[k]))
+    ctx.close()
+
+
+def test_batch_of_mixed_streams(oracle):
+    """Many streams of different structure in one context: lanes of one warp parse slices of
+    different streams, picture types and slice layouts at the same time."""
+    streams = [make(i, kw)[0] for i, (_, kw) in enumerate(COVERAGE) if kw["n_pictures"] == 12]
+    streams += [synth.generate(synth.SEED0 + 50 + i)[0] for i in range(37)]
+    streams.append(np.zeros(0, dtype=np.uint8))                         # empty stream
+    streams.append(streams[0][: streams[0].size // 2].copy())           # ragged: truncated mid-picture
+    n = len(streams)
+    ctx = espflix_b200.Context(n_streams=n, max_pictures=12, es_capacity=1 << 23)
+    blob, off = ctx.pack(streams)
+    ctx.submit_es(blob, off)
+    ctx.index()
+    info = ctx.index_info()
+    assert info["max_pictures"] == 12
+    ctx.decode_all(12)
+    got = ctx.read_latest_i420()
+    for i in range(n - 2):
+        want = oracle.decode_es(streams[i])
+        assert np.array_equal(got[i], want[-1]), "stream %d: %s" % (i, _first_diff(got[i], want[-1]))
+    assert ctx.stream_info(n - 2)[0] == 0
+    assert (got[n - 2] == 0).all()                                      # never-written frame store stays zero (Frame::init)
+    ctx.close()
+
+
+def test_chunked_submits_carry_state(oracle):
+    """Submits cut at GOP boundaries: ping-pong phase and sequence state persist across submits."""
+    es, off = synth.generate(synth.SEED0 + 77, n_pictures=36, gop=12, flags=synth.MATRICES)
+    want = oracle.decode_es(es)
+    ctx = espflix_b200.Context(n_streams=1, max_pictures=13, es_capacity=1 << 22)
+    got = []
+    for a, b in ((0, 12), (12, 25), (25, 36)):                          # uneven cuts, second one mid-GOP
+        got += ctx.decode_sequence([es[off[a]:off[b]]])[0]
+    assert len(got) == 36
+    for k in range(36):
+        assert np.array_equal(got[k], want[k]), "picture %d: %s" % (k, _first_diff(got[k], want[k]))
+    ctx.close()
+
+
+def test_replicated_batch_properties():
+    """config 4 shape at reduced width: D distinct streams replicated R times must give R identical
+    copies (size-independent property: no cross-stream interference in the warp-shared kernel)."""
+    D, R = 16, 24
+    distinct = [synth.generate(synth.SEED0 + i)[0] for i in range(D)]
+    streams = [distinct[i % D] for i in range(D * R)]
+    ctx = espflix_b200.Context(n_streams=D * R, max_pictures=12, es_capacity=1 << 26, fields=False)
+    blob, off = ctx.pack(streams)
+    ctx.submit_es(blob, off)
+    ctx.index()
+    info = ctx.index_info()
+    assert info["total_pictures"] == D * R * 12 and info["total_slices"] == D * R * 12 * 12
+    ctx.decode_all(12)
+    got = ctx.read_latest_i420()
+    for i in range(D, D * R):
+        assert np.array_equal(got[i], got[i % D]), i
+    # decoding the same submit again (next GOP period) is idempotent: I pictures refresh everything
+    ctx.index()
+    ctx.decode_all(12)
+    assert np.array_equal(ctx.read_latest_i420(), got)
+    ctx.close()
+
+
+def test_error_paths():
+    ctx = espflix_b200.Context(n_streams=2, max_pictures=2, es_capacity=4096)
+    with pytest.raises(espflix_b200.EspflixError):
+        ctx.index()                                                     # index before submit
+    blob = np.zeros(8192, dtype=np.uint8)
+    with pytest.raises(espflix_b200.EspflixError):
+        ctx.submit_es(blob, np.array([0, 4096, 8192], dtype=np.uint64))  # exceeds es_capacity
+    es, _ = synth.generate(synth.SEED0, n_pictures=4, gop=4, noise=0)
+    small = espflix_b200.Context(n_streams=1, max_pictures=2, es_capacity=1 << 20)
+    b, o = small.pack([es])
+    small.submit_es(b, o)
+    small.index()
+    with pytest.raises(espflix_b200.EspflixError):
+        small.index_info()                                              # 4 pictures > max_pictures 2
+    small.close()
+    ctx.close()
