@@ -10,6 +10,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libespflix_b200.so")
 SYNTH_LIB = os.path.join(PKG, "synth", "libefsynth.so")
 HOST_LIB = os.path.join(PKG, "host", "libespflix_host.so")
+HOST_CLI = os.path.join(PKG, "host", "ef_player_cli")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libef_oracle.so")
 REF_DECODE = os.path.join(ROOT, "oracle", "_ref", "efref_decode")
 REF_VIDEO = os.path.join(ROOT, "oracle", "_ref", "libefref_vid.so")
@@ -61,8 +62,10 @@ def build_host(force=False):
         return
     deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")]
     if force or _newer(HOST_LIB, deps + [LIB]):
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", HOST_LIB]
-             + srcs + ["-L", PKG, "-lespflix_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"])
+        common = ["-O2", "-std=c++17", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", hdir]
+        link = ["-L", PKG, "-lespflix_b200", "-lpthread"]
+        _run(["g++"] + common + ["-shared", "-o", HOST_LIB] + srcs + link + ["-Wl,-rpath,$ORIGIN/.."])
+        _run(["g++"] + common + ["-o", HOST_CLI, os.path.join(hdir, "ef_player_cli.cpp")] + srcs + link + ["-Wl,-rpath,$ORIGIN/.."])
 
 
 def build_oracle(force=False):

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "ef_read_frame": (_I, [_VP, _I, _I, _VP]),
     "ef_read_frame_i420": (_I, [_VP, _I, _I, _VP]),
     "ef_write_frame_i420": (_I, [_VP, _I, _I, _VP]),
+    "ef_write_frame": (_I, [_VP, _I, _I, _VP]),
     "ef_frame_device_ptr": (_I, [_VP, _I, _I, ctypes.POINTER(_VP)]),
     "ef_read_latest_i420": (_I, [_VP, _I, _I, _VP, _VP]),
     "ef_video_init": (_I, [_VP, _I]),

@@ -434,6 +434,15 @@ int ef_write_frame_i420(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
     return EF_OK;
 }
 
+int ef_write_frame(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
+{
+    if (!c || !src) return fail(EF_EINVAL, "null argument");
+    int f; int rc = resolve_fb(c, stream_index, fb, &f);
+    if (rc != EF_OK) return rc;
+    CK(cudaMemcpy(c->h.frames + ef_frame_offset(stream_index, f), src, EF_FRAME, cudaMemcpyHostToDevice));
+    return EF_OK;
+}
+
 int ef_frame_device_ptr(ef_ctx* c, int stream_index, int fb, void** ptr)
 {
     if (!c || !ptr || stream_index < 0 || stream_index >= c->cfg.n_streams || (fb != 0 && fb != 1)) return fail(EF_EINVAL, "bad argument");
@@ -481,7 +490,7 @@ int ef_composite_field(ef_ctx* c, int fb, int frame_counter, void* stream)
 {
     if (!c) return fail(EF_EINVAL, "null context");
     if (!c->h.fields) return fail(EF_ESTATE, "context was created without field buffers (ef_config.fields = 0)");
-    if (fb < -1 || fb > 1) return fail(EF_EINVAL, "fb must be 0, 1 or -1");
+    if (fb < -2 || fb > 1) return fail(EF_EINVAL, "fb must be 0, 1, -1 or -2");
     CK(ef_launch_composite(c->d, c->cfg.n_streams, c->h.geo, fb, frame_counter, (cudaStream_t)stream));
     c->launches++;
     return EF_OK;

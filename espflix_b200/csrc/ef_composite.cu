@@ -69,7 +69,7 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
     uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)line * g.line_width + x0;
 
     const int fl = line - g.active_top;                                    // frame line 0..191 on active lines
-    const bool active = fl >= 0 && fl < EF_H;
+    const bool active = fl >= 0 && fl < EF_H && fb_sel != -2;      // -2: no frame presented yet (video.cpp:1140)
     uint32_t w[4];
     if (active && x0 >= g.blit_start && x0 < g.blit_start + 2 * EF_W) {
         const int fb = fb_sel >= 0 ? fb_sel : (int)((D.base_pics[stream] + D.n_pics[stream]) & 1u);

@@ -1,0 +1,74 @@
+// espflix_b200/host/ef_player_cli.cpp — drives the mirrored MpegDecoder exactly the way the oracle
+// harness drives the reference one (oracle/ref_decode_harness.cpp; espflix.cpp:723-737 decode_next):
+// pop_empty -> fill Buffer with <= 8 TS packets -> push_full, decoder thread in run(), frames
+// captured from push_video, final flush_picture(1). Usage: ef_player_cli in.ts out.i420 [fields.u16 ntsc]
+#include <stdio.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include "ef_player.h"
+
+static std::vector<uint8_t> g_out;
+static long g_frames = 0;
+
+static void on_push(Frame* f, int front, int64_t, int, void*)
+{
+    Frame* fr = &f[front];
+    size_t o = g_out.size();
+    g_out.resize(o + 352 * 192 * 3 / 2);
+    uint8_t* d = g_out.data() + o;
+    for (int y = 0; y < 192; y++, d += 352) memcpy(d, fr->get_y(y), 352);
+    for (int y = 0; y < 96; y++, d += 176) memcpy(d, fr->get_cr(y), 176);
+    for (int y = 0; y < 96; y++, d += 176) memcpy(d, fr->get_cb(y), 176);
+    g_frames++;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: %s in.ts out.i420 [field.u16 ntsc(1|0)]\n", argv[0]); return 2; }
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) { perror(argv[1]); return 2; }
+    std::vector<uint8_t> ts;
+    uint8_t tmp[65536]; size_t n;
+    while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) ts.insert(ts.end(), tmp, tmp + n);
+    fclose(f);
+
+    ef_set_push_video_hook(on_push, nullptr);
+    Frame fb[2];
+    fb[0].init(); fb[1].init();
+    MpegDecoder dec(&fb[0], &fb[1]);
+    std::thread th([&] { dec.run(); });
+    size_t pos = 0;
+    while (pos + 188 <= ts.size()) {
+        Buffer* b = dec.pop_empty();
+        size_t k = ts.size() - pos;
+        if (k > sizeof(b->data)) k = sizeof(b->data);
+        k -= k % 188;
+        memcpy(b->data, ts.data() + pos, k);
+        b->len = (uint32_t)k;
+        pos += k;
+        dec.push_full(b);
+    }
+    Buffer* b = dec.pop_empty();
+    b->len = 0;
+    dec.push_full(b);
+    th.join();
+    dec.flush_picture(1);
+    FILE* o = fopen(argv[2], "wb");
+    fwrite(g_out.data(), 1, g_out.size(), o);
+    fclose(o);
+    if (argc >= 5) {                               // one field of the last presented frame through video_isr
+        const int ntsc = atoi(argv[4]);
+        video_init(ntsc);
+        const int w = ntsc ? 912 : 1136, lines = ntsc ? 262 : 312;
+        std::vector<uint16_t> field((size_t)w * lines), line(w + 64);
+        for (int l = 0; l < lines; l++) { video_isr(line.data()); memcpy(field.data() + (size_t)l * w, line.data(), (size_t)w * 2); }
+        FILE* ff = fopen(argv[3], "wb");
+        fwrite(field.data(), 2, field.size(), ff);
+        fclose(ff);
+    }
+    printf("{\"frames\": %ld}\n", g_frames);
+    return 0;
+}

@@ -101,6 +101,7 @@ int ef_decode_all(ef_ctx* ctx, int n_pictures, void* stream);
 int ef_read_frame(ef_ctx* ctx, int stream_index, int fb, uint8_t* dst_strips /* EF_FRAME_BYTES */);
 int ef_read_frame_i420(ef_ctx* ctx, int stream_index, int fb, uint8_t* dst /* EF_I420_BYTES */);
 int ef_write_frame_i420(ef_ctx* ctx, int stream_index, int fb, const uint8_t* src);   /* tests / GUI-drawn frames */
+int ef_write_frame(ef_ctx* ctx, int stream_index, int fb, const uint8_t* src_strips /* EF_FRAME_BYTES */);
 /* Device address of a stream's frame store (for zero-copy consumers); fb as above but not -1. */
 int ef_frame_device_ptr(ef_ctx* ctx, int stream_index, int fb, void** ptr);
 /* Batched read-back of the most recent picture of streams [first, first+count) as I420. */
@@ -109,8 +110,9 @@ int ef_read_latest_i420(ef_ctx* ctx, int first, int count, uint8_t* dst, void* s
 /* K2: composite synthesis. */
 int ef_video_init(ef_ctx* ctx, int ntsc);                          /* 1 NTSC, 0 PAL */
 int ef_video_geometry(ef_ctx* ctx, int* line_width, int* line_count);
-/* One field for every stream from frame `fb` (-1 = most recent picture), `frame_counter` = the
- * reference's _frame_counter (dither phase), one launch. */
+/* One field for every stream from frame `fb` (-1 = most recent picture, -2 = no frame presented yet:
+ * active lines come out as blank lines, the reference's _current_frame == -1 case, video.cpp:1140),
+ * `frame_counter` = the reference's _frame_counter (dither phase), one launch. */
 int ef_composite_field(ef_ctx* ctx, int fb, int frame_counter, void* stream);
 int ef_read_field(ef_ctx* ctx, int stream_index, uint16_t* dst /* line_count*line_width */);
 /* video_isr-style single line fetch from the last synthesised field of stream_index. */
