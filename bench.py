@@ -133,15 +133,28 @@ def calibrate_loops(gen, target_s):
     return max(10, int(target_s / max(per_loop, 1e-6)))
 
 
+def best_process_count(gen):
+    """The reference runs a decoder thread plus a producer thread per process; on an SMT host one
+    process per hardware thread can be slower than one per core. Try both briefly, keep the faster."""
+    hw = os.cpu_count() or 1
+    best, best_rate = hw, 0.0
+    loops = calibrate_loops(gen, 1.5)
+    for p in sorted({hw, max(1, hw // 2)}, reverse=True):
+        f, s, _ = cpu_decode_sample(gen, p, loops)
+        if f / s > best_rate:
+            best, best_rate = p, f / s
+    return best
+
+
 def run_reference(args):
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     if rank != 0:
         return 0
     gen, _ = make_streams(DISTINCT)
-    cores = os.cpu_count() or 1
-    total_budget = 120.0
-    per_step = min(20.0, total_budget / max(1, args.steps + args.warmup))
-    loops = calibrate_loops(gen, per_step)
+    cores = best_process_count(gen)
+    total_budget = 100.0
+    per_step = min(15.0, total_budget / max(1, args.steps + args.warmup))
+    loops = max(10, calibrate_loops(gen, per_step) // 3)     # a loaded host runs each process ~3x slower than a lone one
     for _ in range(args.warmup):
         cpu_decode_sample(gen, cores, max(10, loops // 4))
     frames = secs = 0.0
@@ -151,7 +164,7 @@ def run_reference(args):
         frames += f
         secs += s
     value = frames / secs
-    sample = "%d processes x %d loops of one 12-picture synthetic stream each (TS-wrapped, same seeds as the GPU arm)" % (cores, loops)
+    sample = "%d processes (of %d hardware threads) x %d loops of one 12-picture synthetic stream each (TS-wrapped, same seeds as the GPU arm)" % (cores, os.cpu_count() or 1, loops)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -302,11 +315,11 @@ def run_gpu(args):
             "picture_bytes_first_stream": [int(x) for x in sizes],
         }
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            loops = calibrate_loops(gen, 12.0)
+            cores = best_process_count(gen)
+            loops = max(10, calibrate_loops(gen, 12.0) // 3)
             f, s, kind = cpu_decode_sample(gen, cores, loops)
             line["cpu_baseline"] = {"value": f / s, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": "%d processes x %d loops of one 12-picture synthetic stream each (TS-wrapped), %.1f s" % (cores, loops, s)}
+                                    "sample": "%d processes (of %d hardware threads) x %d loops of one 12-picture synthetic stream each (TS-wrapped), %.1f s" % (cores, os.cpu_count() or 1, loops, s)}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:

@@ -47,11 +47,12 @@ int fail(int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(EF_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-// strips layout <-> I420 (video.h:36-44; player.cpp:33-46) — device kernels so that reads stay one copy
-__global__ void ef_strips_to_i420_kernel(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ base_pics,
-                                         const uint32_t* __restrict__ n_pics, int first, int count, int fb_sel, uint8_t* __restrict__ dst)
+// device frame stores are macroblock-tiled (ef_common.cuh); these kernels convert to/from the two
+// host-visible layouts: the I420 dump and the reference's strips (video.h:36-44; player.cpp:33-46).
+// mode 0 = I420, 1 = strips. One thread per 4 bytes (4 consecutive pixels never straddle a tile row).
+__global__ void ef_export_frames_kernel(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ base_pics,
+                                        const uint32_t* __restrict__ n_pics, int first, int count, int fb_sel, int mode, uint8_t* __restrict__ dst)
 {
-    // one thread per 4 output bytes
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t per = EF_FRAME / 4;
     const uint32_t k = (uint32_t)(t / per), w = (uint32_t)(t % per);
@@ -59,31 +60,17 @@ __global__ void ef_strips_to_i420_kernel(const uint8_t* __restrict__ frames, con
     const int s = first + (int)k;
     const int fb = fb_sel >= 0 ? fb_sel : (int)((base_pics[s] + n_pics[s]) & 1u);
     const uint8_t* f = frames + ef_frame_offset(s, fb);
-    const uint32_t b = w * 4;
-    uint32_t src;
-    if (b < EF_W * EF_H) { const uint32_t y = b / EF_W, x = b % EF_W; src = y * EF_STRIDE + x; }
-    else {
-        const uint32_t c = b - EF_W * EF_H;
-        const uint32_t plane = c / (176 * 96), r = c % (176 * 96);
-        const uint32_t y = r / 176, x = r % 176;
-        src = (y >> 3) * 8448 + ((y & 7) + plane * 8) * EF_STRIDE + EF_W + x;
-    }
+    const int b = (int)w * 4;
+    const int src = mode == 0 ? ef_i420_to_tiled(b) : ef_strips_to_tiled(b);
     *(uint32_t*)(dst + (size_t)k * EF_FRAME + b) = *(const uint32_t*)(f + src);
 }
 
-__global__ void ef_i420_to_strips_kernel(uint8_t* __restrict__ frame, const uint8_t* __restrict__ src)
+__global__ void ef_import_frame_kernel(uint8_t* __restrict__ frame, const uint8_t* __restrict__ src, int mode)
 {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= EF_FRAME / 4) return;
-    const uint32_t b = w * 4;
-    uint32_t dst;
-    if (b < EF_W * EF_H) { const uint32_t y = b / EF_W, x = b % EF_W; dst = y * EF_STRIDE + x; }
-    else {
-        const uint32_t c = b - EF_W * EF_H;
-        const uint32_t plane = c / (176 * 96), r = c % (176 * 96);
-        const uint32_t y = r / 176, x = r % 176;
-        dst = (y >> 3) * 8448 + ((y & 7) + plane * 8) * EF_STRIDE + EF_W + x;
-    }
+    const int b = (int)w * 4;
+    const int dst = mode == 0 ? ef_i420_to_tiled(b) : ef_strips_to_tiled(b);
     *(uint32_t*)(frame + dst) = *(const uint32_t*)(src + b);
 }
 
@@ -93,12 +80,9 @@ __global__ void ef_reset_seq_kernel(EfDev* Dp, const uint8_t* default_intra)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D.n_streams) return;
     EfSeq* q = D.seq + (size_t)s * (D.max_seq + 1);
-    for (int e = 0; e < 64; e++) {
-        const int t = (e & 7) * 8 + (e >> 3);
-        q->intra_qT[t] = default_intra[e];
-        q->inter_qT[t] = 16;
-    }
-    q->mb_width = 22; q->mb_height = 12; q->valid = 1; q->pad0 = 0;
+    for (int n = 0; n < 128; n++) q->q_scan[n] = D.tables->qdef[n];
+    (void)default_intra;
+    q->mb_width = 22; q->mb_height = 12; q->valid = 1; q->custom = 0;
     D.n_pics[s] = 0; D.base_pics[s] = 0; D.n_seq[s] = 0;
 }
 
@@ -213,6 +197,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     A(h.work, h.work_capacity);
     A(h.info, 8);
     EfTables* dt; A(dt, 1);
+    A(h.k1_overflow, (size_t)c->sm_count * EF_K1_WARPS * 32 * (384 - EF_K1_LIST));
     A(c->d_color_tab, 768); A(c->d_pal_burst, 128); A(c->d_default_intra, 64);
     if (cfg->fields) { h.field_stride = EF_PAL_FIELD_SAMPLES; A(h.fields, (size_t)n * h.field_stride); }
     A(c->d, 1);
@@ -384,7 +369,12 @@ int ef_read_frame(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
     CK(cudaDeviceSynchronize());
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
     if (rc != EF_OK) return rc;
-    CK(cudaMemcpy(dst, c->h.frames + ef_frame_offset(stream_index, f), EF_FRAME, cudaMemcpyDeviceToHost));
+    rc = ensure_stage(c, EF_FRAME);
+    if (rc != EF_OK) return rc;
+    ef_export_frames_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, 1, c->d_stage);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaMemcpy(dst, c->d_stage, EF_FRAME, cudaMemcpyDeviceToHost));
     return EF_OK;
 }
 
@@ -396,7 +386,7 @@ int ef_read_latest_i420(ef_ctx* c, int first, int count, uint8_t* dst, void* str
     if (rc != EF_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t threads = (uint64_t)count * (EF_FRAME / 4);
-    ef_strips_to_i420_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, c->d_stage);
+    ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, 0, c->d_stage);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaMemcpyAsync(dst, c->d_stage, (size_t)count * EF_FRAME, cudaMemcpyDeviceToHost, st));
@@ -412,7 +402,7 @@ int ef_read_frame_i420(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
     if (rc != EF_OK) return rc;
     rc = ensure_stage(c, EF_FRAME);
     if (rc != EF_OK) return rc;
-    ef_strips_to_i420_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, c->d_stage);
+    ef_export_frames_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, 0, c->d_stage);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaMemcpy(dst, c->d_stage, EF_FRAME, cudaMemcpyDeviceToHost));
@@ -427,7 +417,7 @@ int ef_write_frame_i420(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
     rc = ensure_stage(c, EF_FRAME);
     if (rc != EF_OK) return rc;
     CK(cudaMemcpy(c->d_stage, src, EF_FRAME, cudaMemcpyHostToDevice));
-    ef_i420_to_strips_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames + ef_frame_offset(stream_index, f), c->d_stage);
+    ef_import_frame_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames + ef_frame_offset(stream_index, f), c->d_stage, 0);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaDeviceSynchronize());
@@ -439,7 +429,13 @@ int ef_write_frame(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
     if (!c || !src) return fail(EF_EINVAL, "null argument");
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
     if (rc != EF_OK) return rc;
-    CK(cudaMemcpy(c->h.frames + ef_frame_offset(stream_index, f), src, EF_FRAME, cudaMemcpyHostToDevice));
+    rc = ensure_stage(c, EF_FRAME);
+    if (rc != EF_OK) return rc;
+    CK(cudaMemcpy(c->d_stage, src, EF_FRAME, cudaMemcpyHostToDevice));
+    ef_import_frame_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames + ef_frame_offset(stream_index, f), c->d_stage, 1);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaDeviceSynchronize());
     return EF_OK;
 }
 

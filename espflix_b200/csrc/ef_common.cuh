@@ -4,10 +4,14 @@
 //   es            [es_capacity + 64]            elementary streams of the current submit, back to back
 //   es_off        [n_streams + 1]  u64          byte offset of each stream in `es`
 //   frames        [n_streams][2][101,376]       the reference's two Frame stores per decoder
-//                                               (video.h:36-44). A Frame's 12 strips of 16 rows x 528 B
-//                                               are contiguous, so Y(x,y) = y*528 + x and the chroma
-//                                               columns 352..527 carry block-4 rows in strip rows 0-7
-//                                               and block-5 rows in strip rows 8-15 (player.cpp:33-46).
+//                                               (video.h:36-44), MACROBLOCK-TILED on the device: tile
+//                                               (mx,my) = 384 contiguous bytes at (my*22+mx)*384 =
+//                                               Y[16][16], block-4 chroma [8][8], block-5 chroma [8][8].
+//                                               One macroblock = 12 whole 32-byte sectors, so K1 never
+//                                               writes a partial sector and a motion-compensated read
+//                                               touches at most 4 tiles. ef_read_frame/ef_write_frame
+//                                               convert to/from the reference's strip layout
+//                                               (12 strips x 16 rows x 528 B, player.cpp:33-46).
 //   seq           [n_streams][max_seq+1]        sequence-header state (quantiser matrices, mb_width/height);
 //                                               entry 0 = state carried in from the previous submit
 //   pics          [n_streams][max_pictures]     per picture: type, full_pel, r_size, seq index, first slice
@@ -24,33 +28,39 @@
 #define EF_FRAME 101376
 #define EF_MBW_MAX 22
 #define EF_MBH_MAX 12
+#define EF_TILE 384          // bytes per macroblock tile: 256 Y + 64 + 64 chroma
+#define EF_K1_WARPS 14       // warps per K1 CTA (one CTA per SM; shared-memory bound)
+#define EF_K1_LIST 96        // per-lane coefficient list entries kept in shared memory (rest spills to HBM)
 
 // ---- decode tables (built on the host by ef_tables.cpp from ISO 11172-2 Annex B) -------------
 // All VLC tables are indexed by (leading zeros, next 5 bits) so that one CLZ + one shared-memory
 // load decodes a symbol. Entry formats:
-//   dct:  bits 0-4 code length w/o sign (0 = invalid), 5-9 run, 10-15 level      [12][32] u16
+//   dct:  bits 0-4 code length INCLUDING the sign bit (0 = invalid), 5-9 run, 10-15 level. level 0 marks
+//         the specials: length 2 = end of block ('10'), run 1 = escape. Row 0 holds the dct_coeff_next
+//         forms '10' / '11s'; row 12 replaces row 0 for the first coefficient of a block ('1s').  [13][32] u16
 //   mba:  bits 0-3 length, 4-9 value (1..33, 34 stuffing, 35 escape)             [8][32]  u16
 //   mv:   bits 0-3 length (sign included), 4-9 value+16                          [7][32]  u16
 //   cbp:  bits 0-3 length, 4-9 pattern, indexed by the next 9 bits               [512]    u16
 //   ptype:bits 0-2 length, 3-7 macroblock_type flags, indexed by next 6 bits     [64]     u8
 struct EfTables {
-    uint16_t dct[12 * 32];
+    uint16_t dct[13 * 32];
     uint16_t mba[8 * 32];
     uint16_t mv[7 * 32];
     uint16_t cbp[512];
     uint8_t ptype[64];
+    uint8_t qdef[128];      // default quantiser matrices in SCAN order: [0..63] intra, [64..127] non-intra (all 16)
     uint8_t izz[64];        // raster index -> zig-zag scan position
     uint8_t prescale[64];   // AAN prescale, raster (reference scale_dct_q, player.cpp:161)
-    uint8_t pad[64];
+    uint8_t zigzag[64];     // scan position -> raster index
 };
 
-// sequence state as the decode kernel reads it: matrices transposed ([col][row]) so that a lane
-// that owns one column of an 8x8 block fetches its 8 quantiser entries with one 8-byte load.
+// sequence state as the decode kernel reads it: quantiser matrices in SCAN order (the parser
+// dequantises symbol by symbol), with quirk Q4 already applied: entry n = the byte the reference
+// finds at raster index zigzag[n] of its stream-order copy (player.cpp:646-651, 1113).
 struct __align__(16) EfSeq {
-    uint8_t intra_qT[64];
-    uint8_t inter_qT[64];
+    uint8_t q_scan[128];     // [0..63] intra, [64..127] non-intra
     uint16_t mb_width, mb_height;
-    uint16_t valid, pad0;
+    uint16_t valid, custom;  // custom = a matrix was loaded from the stream (else K1 uses the shared-memory defaults)
     uint32_t pad1[2];
 };
 
@@ -94,6 +104,7 @@ struct EfDev {               // device-visible context (lives in device memory)
     EfWork* work;            // flat, grouped by picture index
     uint32_t* info;          // [8]: 0 max pictures, 1 total pictures, 2 total slices, 3 error flags
     const EfTables* tables;
+    uint32_t* k1_overflow;   // [K1 lanes][384 - EF_K1_LIST] spill area of the per-lane coefficient lists
     uint16_t* fields;        // [n_streams][field_stride]
     const uint32_t* color_tab;   // [768]
     const int16_t* pal_burst;    // [2][64]
@@ -103,3 +114,22 @@ struct EfDev {               // device-visible context (lives in device memory)
 };
 
 static inline __host__ __device__ size_t ef_frame_offset(int stream, int fb) { return ((size_t)stream * 2 + (size_t)fb) * EF_FRAME; }
+static inline __host__ __device__ int ef_tile_offset(int mx, int my) { return (my * EF_MBW_MAX + mx) * EF_TILE; }
+// byte offset inside a tiled frame of luma pixel (x,y) / of chroma plane p (0 = block 4, 1 = block 5) pixel (x,y)
+static inline __host__ __device__ int ef_luma_offset(int x, int y) { return ef_tile_offset(x >> 4, y >> 4) + (y & 15) * 16 + (x & 15); }
+static inline __host__ __device__ int ef_chroma_offset(int p, int x, int y) { return ef_tile_offset(x >> 3, y >> 3) + 256 + p * 64 + (y & 7) * 8 + (x & 7); }
+// byte index in the I420 dump (Y rows, block-4 rows, block-5 rows) -> offset in the tiled frame
+static inline __host__ __device__ int ef_i420_to_tiled(int b)
+{
+    if (b < EF_W * EF_H) return ef_luma_offset(b % EF_W, b / EF_W);
+    const int c = b - EF_W * EF_H, plane = c / (176 * 96), r = c % (176 * 96);
+    return ef_chroma_offset(plane, r % 176, r / 176);
+}
+// byte index in the reference's strip layout (12 contiguous strips of 16 x 528) -> offset in the tiled frame
+static inline __host__ __device__ int ef_strips_to_tiled(int b)
+{
+    const int row = b / EF_STRIDE, x = b % EF_STRIDE;
+    if (x < EF_W) return ef_luma_offset(x, row);
+    const int r = row & 15;
+    return ef_chroma_offset(r >> 3, x - EF_W, (row >> 4) * 8 + (r & 7));
+}

@@ -76,25 +76,27 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
         const uint8_t* f = D.frames + ef_frame_offset((int)stream, fb);
         const int q = (x0 - g.blit_start) >> 3;                            // 4-pixel group index 0..87
         const uint32_t dither = c_dither[(fl & 3) + ((frame_counter & 1) << 2)];
-        const uint32_t* yrow = (const uint32_t*)(f + fl * EF_STRIDE);
+        // tiled frame (ef_common.cuh): 4 luma pixels of group q sit in tile q>>2, the 2 chroma samples too
         const int cy = fl >> 1;
-        const int urow = (cy >> 3) * 8448 + (cy & 7) * EF_STRIDE + EF_W;  // get_cr(line>>1); get_cb is 8 strip rows below
-        uint32_t u2 = *(const uint16_t*)(f + urow + q * 2);
-        uint32_t v2 = *(const uint16_t*)(f + urow + 8 * EF_STRIDE + q * 2);
+        const int ycol = (q >> 2) * EF_TILE + (q & 3) * 4, ccol = (q >> 2) * EF_TILE + 256 + (q & 3) * 2;
+        const uint8_t* yrow = f + (fl >> 4) * EF_MBW_MAX * EF_TILE + (fl & 15) * 16;
+        const uint8_t* crow = f + (cy >> 3) * EF_MBW_MAX * EF_TILE + (cy & 7) * 8;       // get_cr(line>>1); get_cb is the next 64-byte plane
+        uint32_t u2 = *(const uint16_t*)(crow + ccol);
+        uint32_t v2 = *(const uint16_t*)(crow + ccol + 64);
         int vt = 256;
         if (fl & 1) {                                                      // odd lines average with the next chroma row (video.cpp:704-716)
             const int n = cy + (fl == 191 ? 0 : 1);
-            const int nrow = (n >> 3) * 8448 + (n & 7) * EF_STRIDE + EF_W;
-            const uint32_t ub = *(const uint16_t*)(f + nrow + q * 2);
-            const uint32_t vb = *(const uint16_t*)(f + nrow + 8 * EF_STRIDE + q * 2);
+            const uint8_t* nrow = f + (n >> 3) * EF_MBW_MAX * EF_TILE + (n & 7) * 8;
+            const uint32_t ub = *(const uint16_t*)(nrow + ccol);
+            const uint32_t vb = *(const uint16_t*)(nrow + ccol + 64);
             u2 = ((u2 >> 1) & 0x7F7Fu) + ((ub >> 1) & 0x7F7Fu);
             v2 = ((v2 >> 1) & 0x7F7Fu) + ((vb >> 1) & 0x7F7Fu);
             vt = 512;
         }
         const uint32_t ca = chroma_word(tab, u2, v2, vt), cb = chroma_word(tab, u2 >> 8, v2 >> 8, vt);
         uint32_t lum = 0;                                                  // carry = pixel 3 of the previous group, 0 at the line start
-        if (q > 0) lum = ((((yrow[q - 1] + dither) & 0xFCFCFCFCu) >> 2) >> 24);
-        uint32_t p0 = (yrow[q] + dither) & 0xFCFCFCFCu;                    // video.cpp:716-733, verbatim packed arithmetic
+        if (q > 0) lum = ((((*(const uint32_t*)(yrow + ((q - 1) >> 2) * EF_TILE + ((q - 1) & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
+        uint32_t p0 = (*(const uint32_t*)(yrow + ycol) + dither) & 0xFCFCFCFCu;   // video.cpp:716-733, verbatim packed arithmetic
         uint32_t p1 = ((p0 >> 1) + (p0 >> 9)) & 0xFCFCFCFCu;
         p0 >>= 2; p1 >>= 2;
         lum = (((p0 & 0xFF) + lum) >> 1) & 0xFF;
@@ -124,17 +126,19 @@ __global__ void ef_blit_kernel(const EfDev* __restrict__ Dp, int stream, int fb,
     if (q * 4 >= width) return;
     const uint8_t* f = D.frames + ef_frame_offset(stream, fb);
     const uint32_t dither = c_dither[(fl & 3) + ((frame_counter & 1) << 2)];
-    const uint32_t* yrow = (const uint32_t*)(f + fl * EF_STRIDE + x);
+    const int g = (x >> 2) + q;                                            // absolute 4-pixel group index
     const int cy = fl >> 1;
-    const int urow = (cy >> 3) * 8448 + (cy & 7) * EF_STRIDE + EF_W + (x >> 1);
-    uint32_t u2 = *(const uint16_t*)(f + urow + q * 2);
-    uint32_t v2 = *(const uint16_t*)(f + urow + 8 * EF_STRIDE + q * 2);
+    const int ycol = (g >> 2) * EF_TILE + (g & 3) * 4, ccol = (g >> 2) * EF_TILE + 256 + (g & 3) * 2;
+    const uint8_t* yrow = f + (fl >> 4) * EF_MBW_MAX * EF_TILE + (fl & 15) * 16;
+    const uint8_t* crow = f + (cy >> 3) * EF_MBW_MAX * EF_TILE + (cy & 7) * 8;
+    uint32_t u2 = *(const uint16_t*)(crow + ccol);
+    uint32_t v2 = *(const uint16_t*)(crow + ccol + 64);
     int vt = 256;
     if (fl & 1) {
         const int n = cy + (fl == 191 ? 0 : 1);
-        const int nrow = (n >> 3) * 8448 + (n & 7) * EF_STRIDE + EF_W + (x >> 1);
-        const uint32_t ub = *(const uint16_t*)(f + nrow + q * 2);
-        const uint32_t vb = *(const uint16_t*)(f + nrow + 8 * EF_STRIDE + q * 2);
+        const uint8_t* nrow = f + (n >> 3) * EF_MBW_MAX * EF_TILE + (n & 7) * 8;
+        const uint32_t ub = *(const uint16_t*)(nrow + ccol);
+        const uint32_t vb = *(const uint16_t*)(nrow + ccol + 64);
         u2 = ((u2 >> 1) & 0x7F7Fu) + ((ub >> 1) & 0x7F7Fu);
         v2 = ((v2 >> 1) & 0x7F7Fu) + ((vb >> 1) & 0x7F7Fu);
         vt = 512;
@@ -142,8 +146,8 @@ __global__ void ef_blit_kernel(const EfDev* __restrict__ Dp, int stream, int fb,
     const uint32_t* tab = D.color_tab;
     const uint32_t ca = chroma_word(tab, u2, v2, vt), cb = chroma_word(tab, u2 >> 8, v2 >> 8, vt);
     uint32_t lum = 0;
-    if (q > 0) lum = ((((yrow[q - 1] + dither) & 0xFCFCFCFCu) >> 2) >> 24);
-    uint32_t p0 = (yrow[q] + dither) & 0xFCFCFCFCu;
+    if (q > 0) lum = ((((*(const uint32_t*)(yrow + ((g - 1) >> 2) * EF_TILE + ((g - 1) & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
+    uint32_t p0 = (*(const uint32_t*)(yrow + ycol) + dither) & 0xFCFCFCFCu;
     uint32_t p1 = ((p0 >> 1) + (p0 >> 9)) & 0xFCFCFCFCu;
     p0 >>= 2; p1 >>= 2;
     lum = (((p0 & 0xFF) + lum) >> 1) & 0xFF;

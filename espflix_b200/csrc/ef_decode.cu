@@ -8,15 +8,21 @@
 // Mapping (B200-first, not a translation of the reference's single scalar loop):
 //   * unit of work = one slice of one stream (EfWork). VLC parsing is serial inside a slice, so the
 //     parallelism is streams x slices: every LANE of a warp parses a different slice, one
-//     macroblock per iteration, straight out of HBM/L2 (MSB-first 32-bit windows, one funnel
-//     shift per peek, CLZ-indexed shared-memory tables: one load per symbol).
-//   * the parsed macroblock (<= 6 x 64 quantised levels + header) is left in shared memory; then
-//     the whole WARP reconstructs the 32 macroblocks one after another: dequantise + the
-//     reference's integer AAN IDCT with one lane per block column/row (4 luma blocks = 32 lanes),
-//     half-pel motion compensation and the clamped add with one lane per 8-pixel row segment,
-//     8-byte coalescing-friendly stores into the striped frame store.
+//     macroblock per iteration. The macroblock header is parsed by all lanes together; the
+//     coefficients are then decoded by a FLAT per-lane state machine (one symbol per step, lanes
+//     move through their blocks independently): CLZ-indexed shared-memory table -> (run, level,
+//     length) in one load, dequantised on the spot (quirk Q2 included) and appended as a 32-bit
+//     (block, scan position, value) entry to the lane's list in shared memory (96 entries; the rare
+//     longer macroblock spills to a per-lane HBM area).
+//   * then the whole WARP reconstructs the 32 macroblocks one after another: scatter the list into
+//     a dense 6x64 scratch, the reference's integer AAN IDCT with one lane per block column / row
+//     (4 luma blocks = 32 lanes), half-pel motion compensation and the clamped add with one lane
+//     per 8-pixel row segment.
+//   * frame stores are MACROBLOCK-TILED in HBM (ef_common.cuh): a macroblock is 384 contiguous
+//     bytes, so the warp's stores are two full 128-byte lines + one more for chroma, no partial
+//     sectors; motion-compensated reads touch <= 4 tiles.
 //   * lanes that finish a slice pull the next one from a global cursor, so lane occupancy stays
-//     high until the picture's work list is empty (persistent CTAs, one per SM).
+//     high until the picture's work list is empty (persistent CTAs, one per SM, 14 warps).
 // Bit-exactness notes: Q1 clamp [0,248]; Q2 oddification maps 0 -> +1; Q3 chroma
 // vector = floor(luma position / 2); Q4 matrices indexed in raster order (done at index time);
 // Q5 single-coefficient blocks bypass the IDCT with floor; Q6 first macroblock of a slice lands in
@@ -25,23 +31,28 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kRecStride = 804;                 // bytes per lane record; 201 words -> conflict-free lane-strided access
-constexpr int kRecCoef = 0;                     // int16 [6][64] quantised levels, zig-zag order, stored as 2*level+1 (0 = none)
-constexpr int kRecDc = 768;                     // int32 [6] intra DC (pixel scale)
-constexpr int kRecInfo = 792;                   // bit0 valid, bit1 intra, 2-7 coded blocks, 8-13 n==1 mask, 14-19 abort mask (bit b = block b), 20-24 qscale
-constexpr int kRecPos = 796;                    // mb_addr | skip_before << 16
-constexpr int kRecMv = 800;                     // (int16 h) | (int16 v) << 16, half-pel units
+constexpr int kWarpsPerCta = EF_K1_WARPS;
+constexpr int kListEntries = EF_K1_LIST;        // per-lane coefficient list capacity in shared memory
+constexpr int kListBytes = 32 * kListEntries * 4;
+constexpr int kHdrStride = 44;                  // bytes per lane header; 11 words (odd) -> conflict-free
+constexpr int kHdrDc = 0;                       // int32 [6] intra DC (pixel scale)
+constexpr int kHdrInfo = 24;                    // bit0 valid, 1 intra, 2-7 coded blocks, 8-13 n==1 mask, 14-19 abort mask (bit b = block b), 20-24 mb_x, 25-28 mb_y
+constexpr int kHdrCnt = 28;                     // list entries | skip_before << 16
+constexpr int kHdrMv = 32;                      // (int16 h) | (int16 v) << 16, half-pel units
+constexpr int kHdrBytes = 32 * kHdrStride;
+constexpr int kDenseBytes = 6 * 64 * 2;         // int16 [6][64] dequantised coefficients, scan order
 constexpr int kScratchWords = 4 * 72;           // IDCT transpose scratch: 4 blocks x (64 + 8 pad) ints
-constexpr int kWarpBytes = 32 * kRecStride + kScratchWords * 4;
+constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes + kScratchWords * 4;
 
-struct SharedTables {
-    uint16_t dct[12 * 32];
+struct SharedTables {                           // same layout as the head of EfTables
+    uint16_t dct[13 * 32];
     uint16_t mba[8 * 32];
     uint16_t mv[7 * 32];
     uint16_t cbp[512];
     uint8_t ptype[64];
+    uint8_t qdef[128];
 };
+constexpr int kTableBytes = (sizeof(SharedTables) + 15) & ~15;
 
 // ---------------------------------------------------------------------------------------------
 // bit reader (FILL_BITS/peek_bits/get_bits, player.cpp:348-352, 495-514): MSB-first. `hi` holds
@@ -86,12 +97,11 @@ struct BitReader {
 // per-lane slice parser state
 struct SliceState {
     BitReader br;
-    uint32_t stream;
     uint8_t* cur;
     const uint8_t* ref;
-    const EfSeq* seq;
-    int mbw, mbn;            // macroblocks per row / per picture
-    int mb_addr;             // linear address of the last macroblock handled
+    const uint8_t* qcustom;  // stream's scan-order quantiser tables in HBM when they are not the defaults, else null
+    int mbw, mbh;
+    int mb_x, mb_y;          // last macroblock handled
     int first;               // next macroblock is the first of the slice (Q6)
     int ptype, full_pel, r_size;
     int qscale;
@@ -149,15 +159,15 @@ __device__ __forceinline__ void idct8(int (&v)[8])
     }
 }
 
-// dequantise one stored level (block(), player.cpp:1110-1121). s = 2*level+1, never 0 here.
-__device__ __forceinline__ int dequant(int s, bool intra, int qscale, int q, int prescale)
+// dequantise one level (block(), player.cpp:1110-1119): v = 2*level (+-1 when not intra);
+// v = (v * qscale * q) / 16 with C truncation; oddify (Q2: 0 becomes +1); clamp to [-2048, 2047].
+__device__ __forceinline__ int dequant(int level, int intra, int qsq)
 {
-    int v = s - 1;                                  // level << 1
+    int v = level << 1;
     if (!intra) v += v < 0 ? -1 : 1;
-    v = (v * qscale * q) / 16;                      // C division: truncates toward zero
-    if ((v & 1) == 0) v -= v > 0 ? 1 : -1;          // Q2: 0 becomes +1
-    v = max(-2048, min(2047, v));
-    return v * prescale;
+    v = (v * qsq) / 16;
+    if ((v & 1) == 0) v -= v > 0 ? 1 : -1;
+    return max(-2048, min(2047, v));
 }
 
 __device__ __forceinline__ uint32_t pin4(uint32_t pred, int r0, int r1, int r2, int r3)
@@ -182,53 +192,63 @@ __device__ __forceinline__ uint32_t avg4x4(uint32_t a, uint32_t b, uint32_t c, u
     return ((e >> 2) & m) | (((o >> 2) & m) << 8);
 }
 
-// Eight predicted pixels starting at byte offset `off` of the reference frame with half-pel
-// flags; `off2` is the offset of the row below (used when yh). Plain byte semantics of mocomp().
-__device__ __forceinline__ void predict8(const uint8_t* ref, int off, int off2, int xh, int yh, uint32_t& o0, uint32_t& o1)
+// Three consecutive aligned words of one pixel row of a plane in the tiled frame, starting at the
+// word that holds pixel x. kLuma: 16-pixel tile rows, else 8-pixel chroma tile rows (plane 0/1).
+// Plain byte semantics of mocomp(); coordinates are clamped into the frame (the reference reads
+// whatever lies there; in-frame vectors never get here).
+template <bool kLuma>
+__device__ __forceinline__ void row_words(const uint8_t* ref, int plane, int x, int y, uint32_t& w0, uint32_t& w1, uint32_t& w2)
 {
-    off = max(0, min(EF_FRAME - 4, off));
-    off2 = max(0, min(EF_FRAME - 4, off2));
-    const uint32_t* a = (const uint32_t*)(ref + (off & ~3));
-    int sh = (off & 3) * 8;
-    uint32_t w0 = a[0], w1 = a[1], w2 = a[2];
-    uint32_t p0 = __funnelshift_r(w0, w1, sh), p1 = __funnelshift_r(w1, w2, sh);
+    constexpr int W = kLuma ? EF_W : EF_W / 2, H = kLuma ? EF_H : EF_H / 2, TS = kLuma ? 16 : 8, SH = kLuma ? 4 : 3;
+    y = max(0, min(H - 1, y));
+    int xa = max(0, min(W - 4, x & ~3));
+    int xb = min(W - 4, xa + 4), xc = min(W - 4, xa + 8);
+    const int rowbase = (y >> SH) * EF_MBW_MAX * EF_TILE + (kLuma ? 0 : 256 + plane * 64) + (y & (TS - 1)) * TS;
+    w0 = *(const uint32_t*)(ref + rowbase + (xa >> SH) * EF_TILE + (xa & (TS - 1)));
+    w1 = *(const uint32_t*)(ref + rowbase + (xb >> SH) * EF_TILE + (xb & (TS - 1)));
+    w2 = *(const uint32_t*)(ref + rowbase + (xc >> SH) * EF_TILE + (xc & (TS - 1)));
+}
+
+// Eight predicted pixels whose first one is pixel (x, y) of the reference plane, with half-pel flags.
+template <bool kLuma>
+__device__ __forceinline__ void predict8(const uint8_t* ref, int plane, int x, int y, int xh, int yh, uint32_t& o0, uint32_t& o1)
+{
+    const int sh = (x & 3) * 8;
+    uint32_t w0, w1, w2;
+    row_words<kLuma>(ref, plane, x, y, w0, w1, w2);
+    const uint32_t p0 = __funnelshift_r(w0, w1, sh), p1 = __funnelshift_r(w1, w2, sh);
     if (xh) {
-        uint32_t q0 = __funnelshift_rc(w0, w1, sh + 8), q1 = __funnelshift_rc(w1, w2, sh + 8);
+        const uint32_t q0 = __funnelshift_rc(w0, w1, sh + 8), q1 = __funnelshift_rc(w1, w2, sh + 8);
         if (yh) {
-            const uint32_t* b = (const uint32_t*)(ref + (off2 & ~3));
-            int sh2 = (off2 & 3) * 8;
-            uint32_t v0 = b[0], v1 = b[1], v2 = b[2];
-            o0 = avg4x4(p0, q0, __funnelshift_r(v0, v1, sh2), __funnelshift_rc(v0, v1, sh2 + 8));
-            o1 = avg4x4(p1, q1, __funnelshift_r(v1, v2, sh2), __funnelshift_rc(v1, v2, sh2 + 8));
+            uint32_t v0, v1, v2;
+            row_words<kLuma>(ref, plane, x, y + 1, v0, v1, v2);
+            o0 = avg4x4(p0, q0, __funnelshift_r(v0, v1, sh), __funnelshift_rc(v0, v1, sh + 8));
+            o1 = avg4x4(p1, q1, __funnelshift_r(v1, v2, sh), __funnelshift_rc(v1, v2, sh + 8));
         } else {
             o0 = avg2x4(p0, q0);
             o1 = avg2x4(p1, q1);
         }
     } else if (yh) {
-        const uint32_t* b = (const uint32_t*)(ref + (off2 & ~3));
-        int sh2 = (off2 & 3) * 8;
-        uint32_t v0 = b[0], v1 = b[1], v2 = b[2];
-        o0 = avg2x4(p0, __funnelshift_r(v0, v1, sh2));
-        o1 = avg2x4(p1, __funnelshift_r(v1, v2, sh2));
+        uint32_t v0, v1, v2;
+        row_words<kLuma>(ref, plane, x, y + 1, v0, v1, v2);
+        o0 = avg2x4(p0, __funnelshift_r(v0, v1, sh));
+        o1 = avg2x4(p1, __funnelshift_r(v1, v2, sh));
     } else {
         o0 = p0; o1 = p1;
     }
 }
 
-// chroma row address inside a frame (Frame::get_cr / get_cb, player.cpp:38-46); plane 0 = block 4
-__device__ __forceinline__ int chroma_row_off(int plane, int y) { return (y >> 3) * 8448 + ((y & 7) + plane * 8) * 528 + 352; }
-
 // ---------------------------------------------------------------------------------------------
-// parse one macroblock of this lane's slice into its record. Returns false when the slice ended.
+// macroblock header of this lane's slice (player.cpp:1266-1307). Returns false when the slice
+// ended. On success: hdr is filled, `cbp` = blocks to parse (bit b = block b), `intra` set.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool parse_macroblock(SliceState& s, uint8_t* rec, const SharedTables& T)
+__device__ __forceinline__ bool parse_header(SliceState& s, uint8_t* hdr, const SharedTables& T, int& cbp_out, int& intra_out)
 {
     BitReader& br = s.br;
     uint32_t bits = br.peek();
     if ((bits >> 9) == 0) return false;             // slice_done(): next 23 bits are zero (player.cpp:1238)
 
-    // macroblock_address_increment (player.cpp:1267-1275)
-    int increment = 0;
+    int increment = 0;                              // macroblock_address_increment (player.cpp:1267-1275)
     for (;;) {
         bits = br.peek();
         int lz = __clz(bits);
@@ -243,16 +263,13 @@ __device__ __forceinline__ bool parse_macroblock(SliceState& s, uint8_t* rec, co
         break;
     }
     int skip_before = 0;
-    if (s.first) { s.first = 0; s.mb_addr += 1; }   // inc_mb ignores its argument for the first macroblock (Q6)
-    else {
-        if (increment > 1) { s.dc_y = s.dc_cr = s.dc_cb = 128; s.mv_h = s.mv_v = 0; skip_before = increment - 1; }
-        s.mb_addr += increment;
-    }
-    if (s.mb_addr >= s.mbn) return false;           // the reference would write past the frame here
-    const int mb_addr_here = s.mb_addr;
+    if (s.first) { s.first = 0; increment = 1; }    // inc_mb ignores its argument for the first macroblock (Q6)
+    else if (increment > 1) { s.dc_y = s.dc_cr = s.dc_cb = 128; s.mv_h = s.mv_v = 0; skip_before = increment - 1; }
+    s.mb_x += increment;
+    while (s.mb_x >= s.mbw) { s.mb_x -= s.mbw; s.mb_y++; }     // inc_mb(), player.cpp:823
+    if (s.mb_y >= s.mbh) return false;              // the reference would write past the frame here
 
-    // macroblock_type (player.cpp:1292)
-    int mb_type;
+    int mb_type;                                    // macroblock_type (player.cpp:1292)
     bits = br.peek();
     if (s.ptype == 1) {
         if (bits >> 31) { mb_type = 0x01; br.skip(1); }
@@ -264,7 +281,7 @@ __device__ __forceinline__ bool parse_macroblock(SliceState& s, uint8_t* rec, co
         mb_type = (int)(e >> 3);
         br.skip(e & 7);
     }
-    int intra = mb_type & 1;
+    const int intra = mb_type & 1;
     if (mb_type & 0x10) s.qscale = (int)br.get(5);
     int mvh = 0, mvv = 0;
     if (intra) { s.mv_h = s.mv_v = 0; }
@@ -287,85 +304,38 @@ __device__ __forceinline__ bool parse_macroblock(SliceState& s, uint8_t* rec, co
         cbp = (int)(e >> 4);
         br.skip(e & 15);
     }
+    cbp = (int)(__brev((unsigned)cbp) >> 26);       // bit b = block b (the VLC value has block 0 in bit 5)
+    *(uint32_t*)(hdr + kHdrInfo) = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp << 2) | ((uint32_t)s.mb_x << 20) | ((uint32_t)s.mb_y << 25);
+    *(uint32_t*)(hdr + kHdrCnt) = (uint32_t)skip_before << 16;
+    *(uint32_t*)(hdr + kHdrMv) = ((uint32_t)mvh & 0xFFFFu) | ((uint32_t)mvv << 16);
+    cbp_out = cbp; intra_out = intra;
+    return true;
+}
 
-    cbp = (int)(__brev((unsigned)cbp) >> 26);       // from here on bit b = block b (the VLC value has block 0 in bit 5)
-    int n1mask = 0, abortmask = 0;
-    bool derailed = false;
-    int16_t* coef = (int16_t*)(rec + kRecCoef);
-    int* dcs = (int*)(rec + kRecDc);
-    for (int blk = 0; blk < 6; blk++) {
-        if (!((cbp >> blk) & 1)) continue;
-        int16_t* c = coef + blk * 64;
-        int n = 0;
-        if (intra) {                                 // dct_dc_size + differential (player.cpp:1010-1068)
-            bits = br.peek();
-            int dc_size, used, dc;
-            if (blk < 4) {
-                dc = s.dc_y;
-                if (!(bits >> 31)) { dc_size = 1 + (int)((bits >> 30) & 1); used = 2; }
-                else if (!((bits >> 30) & 1)) { dc_size = ((bits >> 29) & 1) ? 3 : 0; used = 3; }
-                else { int ones = min(9, __clz(~bits)); dc_size = ones + 2; used = dc_size - 1; }
-            } else {
-                dc = blk == 4 ? s.dc_cr : s.dc_cb;
-                if (!(bits >> 31)) { dc_size = (int)((bits >> 30) & 1); used = 2; }
-                else { int ones = min(10, __clz(~bits)); dc_size = ones + 1; used = min(dc_size, 10); }
-            }
-            br.skip(used);
-            if (dc_size) {
-                int delta = (int)br.get(dc_size);
-                if (delta & (1 << (dc_size - 1))) dc += delta;
-                else dc += (int)((0xFFFFFFFFu << dc_size) | (uint32_t)(delta + 1));
-                if (blk < 4) s.dc_y = dc; else if (blk == 4) s.dc_cr = dc; else s.dc_cb = dc;
-            }
-            dcs[blk] = dc;
-            n = 1;
-        }
-        for (;;) {                                   // AC coefficients (player.cpp:1070-1122)
-            bits = br.peek();
-            int run, level, used;
-            if (bits >> 31) {
-                if (n) {
-                    if (!((bits >> 30) & 1)) { br.skip(2); break; }     // '10' end of block
-                    used = 3; level = ((bits >> 29) & 1) ? -1 : 1;       // '11s'
-                } else { used = 2; level = ((bits >> 30) & 1) ? -1 : 1; }   // '1s' first coefficient
-                run = 0;
-            } else {
-                int lz = __clz(bits);
-                if (lz == 5) {                       // escape: 6-bit run, 8- or 16-bit level (player.cpp:1092)
-                    run = (int)((bits >> 20) & 63);
-                    int b = (int)((bits >> 12) & 255);
-                    if (b == 0) { level = (int)((bits >> 4) & 255); used = 28; }
-                    else if (b == 128) { level = (int)((bits >> 4) & 255) - 256; used = 28; }
-                    else { level = (int)(int8_t)b; used = 20; }
-                } else {
-                    if (lz > 11) { derailed = true; break; }             // not a code: the reference derails here
-                    uint32_t e = T.dct[lz * 32 + ((bits << (lz + 1)) >> 27)];
-                    int len = e & 31;
-                    if (!len) { derailed = true; break; }
-                    run = (int)((e >> 5) & 31);
-                    level = (int)(e >> 10);
-                    if ((bits >> (31 - len)) & 1) level = -level;
-                    used = len + 1;
-                }
-            }
-            br.skip(used);
-            n += run;
-            if (n >= 64) { abortmask |= 1 << blk; break; }              // block() returns -1: nothing is stored
-            c[n++] = (int16_t)(2 * level + 1);
-        }
-        if (derailed) {                              // give up on this and the remaining blocks, end the slice
-            abortmask |= 0x3F & ~((1 << blk) - 1);
-            s.mb_addr = s.mbn;
-            break;
-        }
-        if (n == 1) n1mask |= 1 << blk;
+// dct_dc_size + differential of an intra block (player.cpp:1010-1068); returns the DC (pixel scale)
+__device__ __forceinline__ int parse_dc(SliceState& s, int blk)
+{
+    BitReader& br = s.br;
+    const uint32_t bits = br.peek();
+    int dc_size, used, dc;
+    if (blk < 4) {
+        dc = s.dc_y;
+        if (!(bits >> 31)) { dc_size = 1 + (int)((bits >> 30) & 1); used = 2; }
+        else if (!((bits >> 30) & 1)) { dc_size = ((bits >> 29) & 1) ? 3 : 0; used = 3; }
+        else { int ones = min(9, __clz(~bits)); dc_size = ones + 2; used = dc_size - 1; }
+    } else {
+        dc = blk == 4 ? s.dc_cr : s.dc_cb;
+        if (!(bits >> 31)) { dc_size = (int)((bits >> 30) & 1); used = 2; }
+        else { int ones = min(10, __clz(~bits)); dc_size = ones + 1; used = min(dc_size, 10); }
     }
-    uint32_t info = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp << 2) | ((uint32_t)n1mask << 8) |
-                    ((uint32_t)abortmask << 14) | ((uint32_t)(s.qscale & 31) << 20);
-    *(uint32_t*)(rec + kRecInfo) = info;
-    *(uint32_t*)(rec + kRecPos) = (uint32_t)mb_addr_here | ((uint32_t)skip_before << 16);
-    *(uint32_t*)(rec + kRecMv) = ((uint32_t)mvh & 0xFFFFu) | ((uint32_t)mvv << 16);
-    return true;   // a derailed macroblock is still emitted; the slice then ends at the next call (mb_addr == mbn)
+    br.skip(used);
+    if (dc_size) {
+        int delta = (int)br.get(dc_size);
+        if (delta & (1 << (dc_size - 1))) dc += delta;
+        else dc += (int)((0xFFFFFFFFu << dc_size) | (uint32_t)(delta + 1));
+        if (blk < 4) s.dc_y = dc; else if (blk == 4) s.dc_cr = dc; else s.dc_cb = dc;
+    }
+    return dc;
 }
 
 }  // namespace
@@ -376,16 +346,19 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     extern __shared__ __align__(16) uint8_t smem[];
     SharedTables& T = *(SharedTables*)smem;
     const EfDev& D = *Dp;
-    {   // stage the VLC tables (the first sizeof(SharedTables) bytes of EfTables have the same layout)
+    {   // stage the tables (the first sizeof(SharedTables) bytes of EfTables have the same layout)
         const uint32_t* src = (const uint32_t*)D.tables;
         uint32_t* dst = (uint32_t*)smem;
         for (int i = threadIdx.x; i < (int)(sizeof(SharedTables) / 4); i += blockDim.x) dst[i] = src[i];
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t* wbase = smem + ((sizeof(SharedTables) + 15) & ~15) + (size_t)warp * kWarpBytes;
-    uint8_t* rec = wbase + lane * kRecStride;
-    int* scratch = (int*)(wbase + 32 * kRecStride);
-    for (int i = 0; i < kRecStride / 4; i++) ((uint32_t*)rec)[i] = 0;
+    uint8_t* wbase = smem + kTableBytes + (size_t)warp * kWarpBytes;
+    uint32_t* list = (uint32_t*)wbase + lane * kListEntries;
+    uint8_t* hdr = wbase + kListBytes + lane * kHdrStride;
+    int16_t* dense = (int16_t*)(wbase + kListBytes + kHdrBytes);
+    int* scratch = (int*)(wbase + kListBytes + kHdrBytes + kDenseBytes);
+    uint32_t* ovf = D.k1_overflow + ((size_t)(blockIdx.x * kWarpsPerCta + warp) * 32 + lane) * (384 - kListEntries);
+    for (int i = lane; i < kDenseBytes / 4; i += 32) ((uint32_t*)dense)[i] = 0;
     __syncthreads();
 
     const uint32_t total = D.pic_total[pic];
@@ -398,12 +371,13 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     const int prow = lane >> 1, phalf = lane & 1;   // luma pixel row / 8-pixel half owned for prediction + store
     const int rblk = (prow >> 3) * 2 + phalf;       // block that those pixels belong to
     const int rrow = prow & 7;                      // row of that block
+    const int crow = lane & 7, cplane = (lane >> 3) & 1;   // chroma row / plane owned by lanes 0..15
     uint8_t izz[8], psc[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) { izz[r] = D.tables->izz[r * 8 + col]; psc[r] = D.tables->prescale[r * 8 + col]; }
 
     SliceState s;
-    s.first = 0; s.stream = 0; s.cur = nullptr; s.ref = nullptr; s.seq = nullptr;
+    s.first = 0; s.cur = nullptr; s.ref = nullptr; s.qcustom = nullptr; s.mbw = 0;
     bool active = false, exhausted = false;
 
     for (;;) {
@@ -418,24 +392,23 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                 uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1));
                 if (idx >= total) exhausted = true;
                 else {
-                    EfWork w = work[idx];
+                    const EfWork w = work[idx];
                     const int code = w.info & 255;
-                    s.stream = w.stream;
                     s.ptype = (w.info >> 8) & 7; s.full_pel = (w.info >> 11) & 1; s.r_size = (w.info >> 12) & 7;
-                    s.seq = D.seq + (size_t)w.stream * (D.max_seq + 1) + (w.info >> 16);
-                    s.mbw = min((int)s.seq->mb_width, EF_MBW_MAX);
-                    int mbh = min((int)s.seq->mb_height, EF_MBH_MAX);
-                    s.mbn = s.mbw * mbh;
+                    const EfSeq* seq = D.seq + (size_t)w.stream * (D.max_seq + 1) + (w.info >> 16);
+                    s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
+                    s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
+                    s.qcustom = seq->custom ? seq->q_scan : nullptr;
                     const uint32_t fb = (D.base_pics[w.stream] + (uint32_t)pic + 1u) & 1u;     // flush_picture(), player.cpp:692
                     s.cur = D.frames + ef_frame_offset((int)w.stream, (int)fb);
                     s.ref = D.frames + ef_frame_offset((int)w.stream, (int)(fb ^ 1u));
                     const uint8_t* es = D.es + D.es_off[w.stream];
                     const uint8_t* stop = D.es + D.es_off[w.stream + 1];
                     s.br.init(es + w.es_off, stop);
-                    s.mb_addr = (code - 1) * s.mbw - 1;      // slice(): row = code-1, first increment lands on column 0
+                    s.mb_y = code - 2; s.mb_x = s.mbw - 1;   // slice(), player.cpp:1255: the first increment lands on column 0 of row code-1
                     s.first = 1;
                     s.dc_y = s.dc_cr = s.dc_cb = 128; s.mv_h = s.mv_v = 0;
-                    active = code >= 1 && code <= mbh && s.mbw > 0 && s.seq->valid;
+                    active = code >= 1 && code <= s.mbh && s.mbw > 0 && seq->valid;
                     if (active) {
                         s.qscale = (int)s.br.get(5);
                         while (s.br.get(1)) s.br.skip(8);    // extra_information_slice
@@ -445,11 +418,71 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
         }
         if (__all_sync(0xFFFFFFFFu, !active)) break;
 
-        // ---- phase 1: every lane parses one macroblock of its own slice -------------------------
+        // ---- phase 1a: every lane parses the header of the next macroblock of its slice ---------
         bool have = false;
+        int cbp_rem = 0, intra = 0;
         if (active) {
-            have = parse_macroblock(s, rec, T);
+            have = parse_header(s, hdr, T, cbp_rem, intra);
             if (!have) active = false;
+        }
+
+        // ---- phase 1b: flat coefficient state machine, one VLC symbol per lane per step ----------
+        int cnt = 0, n1mask = 0, abortmask = 0, blk = 0, n = 0;
+        bool busy = have && cbp_rem != 0, start = true;
+        const int qsbase = intra ? 0 : 64;
+        while (__any_sync(0xFFFFFFFFu, busy)) {
+            if (busy) {
+                BitReader& br = s.br;
+                if (start) {                                   // next coded block of this macroblock
+                    blk = __ffs(cbp_rem) - 1;
+                    cbp_rem &= cbp_rem - 1;
+                    n = 0;
+                    if (intra) { ((int*)(hdr + kHdrDc))[blk] = parse_dc(s, blk); n = 1; }
+                    start = false;
+                }
+                const uint32_t bits = br.peek();
+                const int lz = __clz(bits);
+                uint32_t e = 0;
+                if (lz <= 11) e = T.dct[((n == 0 && lz == 0) ? 384 : lz * 32) + ((bits << (lz + 1)) >> 27)];
+                int len = e & 31, run = (e >> 5) & 31, level = (int)(e >> 10);
+                bool end_block = false, derail = false;
+                if (level) {
+                    if ((bits >> (32 - len)) & 1) level = -level;
+                } else if (len == 2) {                         // '10': end of block (player.cpp:1075)
+                    end_block = true;
+                    if (n == 1) n1mask |= 1 << blk;            // Q5
+                } else if (run == 1) {                         // escape: 6-bit run, 8- or 16-bit level (player.cpp:1092)
+                    run = (int)((bits >> 20) & 63);
+                    const int b = (int)((bits >> 12) & 255);
+                    if (b == 0) { level = (int)((bits >> 4) & 255); len = 28; }
+                    else if (b == 128) { level = (int)((bits >> 4) & 255) - 256; len = 28; }
+                    else { level = (int)(int8_t)b; len = 20; }
+                } else derail = true;                          // not a code: the reference derails here
+                if (derail) {                                  // give up on this and the remaining blocks, end the slice
+                    abortmask |= (1 << blk) | cbp_rem;
+                    s.mb_y = s.mbh;
+                    busy = false;
+                } else {
+                    br.skip(len);
+                    if (!end_block) {
+                        n += run;
+                        if (n >= 64) { abortmask |= 1 << blk; end_block = true; }      // block() returns -1: nothing is stored
+                        else {
+                            int q;
+                            if (s.qcustom) q = __ldg(s.qcustom + qsbase + n); else q = T.qdef[qsbase + n];
+                            const int v = dequant(level, intra, s.qscale * q);
+                            const uint32_t ent = ((uint32_t)v & 0xFFFFu) | ((uint32_t)n << 16) | ((uint32_t)blk << 22);
+                            if (cnt < kListEntries) list[cnt] = ent; else ovf[cnt - kListEntries] = ent;
+                            cnt++; n++;
+                        }
+                    }
+                    if (end_block) { start = true; busy = cbp_rem != 0; }
+                }
+            }
+        }
+        if (have) {
+            *(uint32_t*)(hdr + kHdrInfo) |= ((uint32_t)n1mask << 8) | ((uint32_t)abortmask << 14);
+            *(uint32_t*)(hdr + kHdrCnt) |= (uint32_t)cnt;
         }
         unsigned todo = __ballot_sync(0xFFFFFFFFu, have);
         __syncwarp();
@@ -458,53 +491,55 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
         while (todo) {
             const int r = __ffs(todo) - 1;
             todo &= todo - 1;
-            uint8_t* R = wbase + r * kRecStride;
-            const uint32_t info = *(const uint32_t*)(R + kRecInfo);
-            const uint32_t posw = *(const uint32_t*)(R + kRecPos);
-            const uint32_t mvw = *(const uint32_t*)(R + kRecMv);
+            const uint8_t* H = wbase + kListBytes + r * kHdrStride;
+            const uint32_t info = *(const uint32_t*)(H + kHdrInfo);
+            const uint32_t cntw = *(const uint32_t*)(H + kHdrCnt);
+            const uint32_t mvw = *(const uint32_t*)(H + kHdrMv);
             uint8_t* cur = (uint8_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)s.cur, r);
             const uint8_t* ref = (const uint8_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)s.ref, r);
-            const EfSeq* seq = (const EfSeq*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)s.seq, r);
+            const uint32_t* rovf = (const uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)ovf, r);
             const int mbw = __shfl_sync(0xFFFFFFFFu, s.mbw, r);
-            const bool intra = (info >> 1) & 1;
-            const int cbp = (info >> 2) & 63, n1mask = (info >> 8) & 63, abortmask = (info >> 14) & 63;
-            const int qscale = (info >> 20) & 31;
-            const int mb_addr = posw & 0xFFFF, skip_before = posw >> 16;
+            const bool intra_r = (info >> 1) & 1;
+            const int cbp = (info >> 2) & 63, n1m = (info >> 8) & 63, abm = (info >> 14) & 63;
+            const int mx = (info >> 20) & 31, my = (info >> 25) & 15;
+            const int entries = cntw & 0xFFFF, skip_before = cntw >> 16;
+            const int live = cbp & ~abm;
+
+            // expand the coefficient list into the dense scratch
+            const uint32_t* rl = (const uint32_t*)wbase + r * kListEntries;
+            for (int j = lane; j < entries; j += 32) {
+                const uint32_t ent = j < kListEntries ? rl[j] : rovf[j - kListEntries];
+                dense[((ent >> 22) & 7) * 64 + ((ent >> 16) & 63)] = (int16_t)(ent & 0xFFFF);
+            }
 
             // skipped macroblocks: predict_zero() copies them from the reference frame (player.cpp:1283-1288)
-            for (int k = skip_before; k > 0; k--) {
-                const int a = mb_addr - k;
-                const int mx = a % mbw, my = a / mbw;
-                const int yo = (my * 16 + prow) * EF_STRIDE + mx * 16 + phalf * 8;
-                *(uint2*)(cur + yo) = *(const uint2*)(ref + yo);
-                if (lane < 16) {
-                    const int co = (my * 16 + lane) * EF_STRIDE + EF_W + mx * 8;    // strip rows 0-7 block 4, 8-15 block 5
-                    *(uint2*)(cur + co) = *(const uint2*)(ref + co);
+            if (skip_before) {
+                int sx = mx, sy = my;
+                for (int k = 0; k < skip_before; k++) {
+                    if (--sx < 0) { sx = mbw - 1; sy--; }
+                    if (sy < 0) break;
+                    const int to = ef_tile_offset(sx, sy);
+                    if (lane < 24) *(uint4*)(cur + to + lane * 16) = *(const uint4*)(ref + to + lane * 16);
                 }
             }
 
-            const int mx = mb_addr % mbw, my = mb_addr / mbw;
             const int mvh = (int)(int16_t)(mvw & 0xFFFF), mvv = (int)(int16_t)(mvw >> 16);
+            const int tile = ef_tile_offset(mx, my);
 
             // ---- prediction: 8 luma pixels per lane, 8 chroma pixels for lanes 0..15 ------------
             uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
-            const int crow = lane & 7, cplane = (lane >> 3) & 1;
-            if (!intra) {
+            if (!intra_r) {
                 const int hx = mx * 32 + mvh, hy = my * 32 + mvv;
-                const int yo = ((hy >> 1) + prow) * EF_STRIDE + (hx >> 1) + phalf * 8;
-                predict8(ref, yo, yo + EF_STRIDE, hx & 1, hy & 1, py0, py1);
+                predict8<true>(ref, 0, (hx >> 1) + phalf * 8, (hy >> 1) + prow, hx & 1, hy & 1, py0, py1);
                 if (lane < 16) {
                     const int cx = hx >> 1, cy = hy >> 1;                           // Q3: floor
-                    const int y0 = (cy >> 1) + crow;
-                    const int o1 = chroma_row_off(cplane, y0) + (cx >> 1);
-                    const int o2 = chroma_row_off(cplane, y0 + 1) + (cx >> 1);
-                    predict8(ref, o1, o2, cx & 1, cy & 1, pc0, pc1);
+                    predict8<false>(ref, cplane, cx >> 1, (cy >> 1) + crow, cx & 1, cy & 1, pc0, pc1);
                 }
             }
+            __syncwarp();                                                           // dense[] complete
 
-            // ---- residual: luma set (blocks 0-3, cbp bits 5..2), then chroma set (blocks 4,5) ---
-            const int16_t* coef = (const int16_t*)(R + kRecCoef);
-            const int* dcs = (const int*)(R + kRecDc);
+            // ---- residual: luma set (blocks 0-3), then chroma set (blocks 4,5) ---------------------
+            const int* dcs = (const int*)(H + kHdrDc);
             int resY[8], resC[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) { resY[i] = 0; resC[i] = 0; }
@@ -512,23 +547,17 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
 #pragma unroll
             for (int set = 0; set < 2; set++) {
                 const int setmask = set == 0 ? 0x0F : 0x30;
-                if (!(cbp & setmask & ~abortmask)) continue;            // warp-uniform
-                const int blk = set == 0 ? cblk : 4 + (cblk & 1);
+                if (!(live & setmask)) continue;                         // warp-uniform
+                const int bk = set == 0 ? cblk : 4 + (cblk & 1);
                 const bool lane_on = set == 0 || lane < 16;
-                const bool coded = lane_on && ((cbp & ~abortmask) >> blk) & 1;
-                const bool full = coded && !((n1mask >> blk) & 1);
+                const bool full = lane_on && ((live & ~n1m) >> bk) & 1;
                 int v[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = 0;
                 if (full) {
-                    const uint2 qv = *(const uint2*)((intra ? seq->intra_qT : seq->inter_qT) + col * 8);
 #pragma unroll
-                    for (int rr = 0; rr < 8; rr++) {
-                        const int sv = coef[blk * 64 + izz[rr]];
-                        const int q = (int)(((rr < 4 ? qv.x : qv.y) >> ((rr & 3) * 8)) & 255);
-                        if (sv) v[rr] = dequant(sv, intra, qscale, q, psc[rr]);
-                    }
-                    if (intra && col == 0) v[0] = (int)((uint32_t)dcs[blk] << 8);   // b[0] <<= 8, player.cpp:1065
+                    for (int rr = 0; rr < 8; rr++) v[rr] = (int)dense[bk * 64 + izz[rr]] * (int)psc[rr];     // b[zz] = v * scale_dct_q[zz]
+                    if (intra_r && col == 0) v[0] = (int)((uint32_t)dcs[bk] << 8);      // b[0] <<= 8, player.cpp:1065
                     idct8<false>(v);
                 }
                 int* Tb = scratch + cblk * 72;
@@ -538,11 +567,11 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                 }
                 __syncwarp();
                 // row pass: luma lanes own (rblk, rrow); chroma lanes 0..15 own (4 + lane/8, lane%8)
-                const int ob = set == 0 ? rblk : (lane >> 3) & 1;          // scratch slot of the row this lane owns
-                const int orow = set == 0 ? rrow : (lane & 7);
-                const int oblk = set == 0 ? rblk : 4 + ((lane >> 3) & 1);
-                const bool ocoded = lane_on && ((cbp & ~abortmask) >> oblk) & 1;
-                const bool ofull = ocoded && !((n1mask >> oblk) & 1);
+                const int ob = set == 0 ? rblk : cplane;                  // scratch slot of the row this lane owns
+                const int orow = set == 0 ? rrow : crow;
+                const int oblk = set == 0 ? rblk : 4 + cplane;
+                const bool ocoded = lane_on && (live >> oblk) & 1;
+                const bool ofull = ocoded && !((n1m >> oblk) & 1);
                 int w[8];
                 {
                     const int4 a = *(const int4*)(scratch + ob * 72 + orow * 8);
@@ -551,14 +580,8 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                 }
                 __syncwarp();
                 if (ofull) idct8<true>(w);
-                else if (ocoded) {                                       // n == 1: dc = b[0] >> 8 (Q5)
-                    int dc;
-                    if (intra) dc = dcs[oblk];
-                    else {
-                        const int sv = coef[oblk * 64];
-                        const int q = (int)seq->inter_qT[0];
-                        dc = dequant(sv, false, qscale, q, 32) >> 8;
-                    }
+                else if (ocoded) {                                       // n == 1: dc = b[0] >> 8 (Q5); scale_dct_q[0] = 32
+                    const int dc = intra_r ? dcs[oblk] : ((int)dense[oblk * 64] * 32) >> 8;
 #pragma unroll
                     for (int i = 0; i < 8; i++) w[i] = dc;
                 }
@@ -573,49 +596,49 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
 
             // ---- combine + store (copy_block / copy_block_dc / add_block / add_block_dc) --------
             {
-                const int blk = rblk;
-                const bool coded = (cbp >> blk) & 1, aborted = (abortmask >> blk) & 1, n1 = (n1mask >> blk) & 1;
+                const bool coded = (cbp >> rblk) & 1, aborted = (abm >> rblk) & 1, n1 = (n1m >> rblk) & 1;
                 uint32_t o0 = py0, o1 = py1;
                 bool store = true;
                 if (coded && !aborted) {
-                    if (intra && n1) {                                   // copy_block_dc: replicated, not clamped (Q7)
+                    if (intra_r && n1) {                                 // copy_block_dc: replicated, not clamped (Q7)
                         uint32_t d = (uint32_t)resY[0]; d |= d << 8; d |= d << 16;
                         o0 = o1 = d;
                     } else {
                         o0 = pin4(py0, resY[0], resY[1], resY[2], resY[3]);
                         o1 = pin4(py1, resY[4], resY[5], resY[6], resY[7]);
                     }
-                } else if (intra) store = false;                          // aborted intra block: destination untouched
-                if (store) *(uint2*)(cur + (my * 16 + prow) * EF_STRIDE + mx * 16 + phalf * 8) = make_uint2(o0, o1);
+                } else if (intra_r) store = false;                        // aborted intra block: destination untouched
+                if (store) *(uint2*)(cur + tile + prow * 16 + phalf * 8) = make_uint2(o0, o1);
             }
             if (lane < 16) {
-                const int blk = 4 + cplane;
-                const bool coded = (cbp >> blk) & 1, aborted = (abortmask >> blk) & 1, n1 = (n1mask >> blk) & 1;
+                const int bk = 4 + cplane;
+                const bool coded = (cbp >> bk) & 1, aborted = (abm >> bk) & 1, n1 = (n1m >> bk) & 1;
                 uint32_t o0 = pc0, o1 = pc1;
                 bool store = true;
                 if (coded && !aborted) {
-                    if (intra && n1) {
+                    if (intra_r && n1) {
                         uint32_t d = (uint32_t)resC[0]; d |= d << 8; d |= d << 16;
                         o0 = o1 = d;
                     } else {
                         o0 = pin4(pc0, resC[0], resC[1], resC[2], resC[3]);
                         o1 = pin4(pc1, resC[4], resC[5], resC[6], resC[7]);
                     }
-                } else if (intra) store = false;
-                if (store) *(uint2*)(cur + (my * 16 + cplane * 8 + crow) * EF_STRIDE + EF_W + mx * 8) = make_uint2(o0, o1);
+                } else if (intra_r) store = false;
+                if (store) *(uint2*)(cur + tile + 256 + cplane * 64 + crow * 8) = make_uint2(o0, o1);
             }
 
-            // ---- clear the coefficient slots this macroblock used (parser invariant: all zero) --
-#pragma unroll
-            for (int b = 0; b < 6; b++)
-                if ((cbp >> b) & 1) ((uint32_t*)(R + kRecCoef))[b * 32 + lane] = 0;
+            // ---- clear the dense slots this macroblock used --------------------------------------
+            for (int j = lane; j < entries; j += 32) {
+                const uint32_t ent = j < kListEntries ? rl[j] : rovf[j - kListEntries];
+                dense[((ent >> 22) & 7) * 64 + ((ent >> 16) & 63)] = 0;
+            }
             __syncwarp();
         }
     }
 }
 
 // host-side launch helper ------------------------------------------------------------------------
-size_t ef_decode_smem_bytes() { return ((sizeof(SharedTables) + 15) & ~(size_t)15) + (size_t)kWarpsPerCta * kWarpBytes; }
+size_t ef_decode_smem_bytes() { return (size_t)kTableBytes + (size_t)kWarpsPerCta * kWarpBytes; }
 int ef_decode_threads() { return kWarpsPerCta * 32; }
 
 cudaError_t ef_decode_configure()

@@ -126,18 +126,19 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
                         const uint64_t after_intra = hb + 63 + (load_intra ? 512 : 0);
                         const uint32_t load_inter = bits_at(es, len, after_intra, 1);
                         EfSeq* q = seqs + k;
-                        for (int e = lane; e < 64; e += 32) {
-                            // Q4: the decoder keeps the 64 bytes in stream order and indexes them with the raster index
-                            const uint32_t qi = load_intra ? bits_at(es, len, hb + 63 + 8 * e, 8) : c_default_intra_q[e];
-                            const uint32_t qn = load_inter ? bits_at(es, len, after_intra + 1 + 8 * e, 8) : 16u;
-                            const int t = (e & 7) * 8 + (e >> 3);                 // transposed: [col][row]
-                            q->intra_qT[t] = (uint8_t)qi;
-                            q->inter_qT[t] = (uint8_t)qn;
+                        for (int n = lane; n < 64; n += 32) {
+                            // Q4: the decoder keeps the 64 bytes in stream order and indexes them with the raster
+                            // index zz = zigzag[n]; the tables here are stored per scan position n
+                            const int zz = D.tables->zigzag[n];
+                            const uint32_t qi = load_intra ? bits_at(es, len, hb + 63 + 8 * zz, 8) : c_default_intra_q[zz];
+                            const uint32_t qn = load_inter ? bits_at(es, len, after_intra + 1 + 8 * zz, 8) : 16u;
+                            q->q_scan[n] = (uint8_t)qi;
+                            q->q_scan[64 + n] = (uint8_t)qn;
                         }
                         if (lane == 0) {
                             q->mb_width = (uint16_t)((hsize + 15) >> 4);
                             q->mb_height = (uint16_t)((vsize + 15) >> 4);
-                            q->valid = 1; q->pad0 = 0;
+                            q->valid = 1; q->custom = (uint16_t)((load_intra || load_inter) ? 1 : 0);
                         }
                     }
                 } else if (code == 0xB7) {                                    // sequence end: the reference decoder parks in pause()

@@ -40,10 +40,13 @@ int ef_build_tables(EfTables* t)
     memset(t, 0, sizeof(*t));
     for (int i = 0; i < EF_VLC_DCT_COUNT; i++) {
         int run = ef_vlc_dct[i].value >> 8, level = ef_vlc_dct[i].value & 0xFF;
-        if (run == 0 && level == 1) continue;           // '1s' / '11s' are handled before the table
-        int len = (int)strlen(ef_vlc_dct[i].code);
+        int len = (int)strlen(ef_vlc_dct[i].code) + 1;                 // + sign bit
+        // (0,1) is "11s" as dct_coeff_next: lives in row 0 next to end-of-block "10"
         if (!place(t->dct, 12, ef_vlc_dct[i].code, (uint16_t)(len | (run << 5) | (level << 10)))) return 1;
     }
+    if (!place(t->dct, 12, "10", (uint16_t)2)) return 1;               // end of block: level 0, length 2
+    if (!place(t->dct, 12, "000001", (uint16_t)(6 | (1 << 5)))) return 1;   // escape: level 0, run 1
+    for (int i = 0; i < 32; i++) t->dct[12 * 32 + i] = (uint16_t)(2 | (0 << 5) | (1 << 10));   // first coefficient: "1s" = (0,1)
     for (int i = 0; i < EF_VLC_MBA_COUNT; i++) {
         int len = (int)strlen(ef_vlc_mba[i].code);
         if (!place(t->mba, 8, ef_vlc_mba[i].code, (uint16_t)(len | (ef_vlc_mba[i].value << 4)))) return 2;
@@ -76,6 +79,8 @@ int ef_build_tables(EfTables* t)
     }
     for (int i = 0; i < 64; i++) t->izz[ef_zigzag[i]] = (uint8_t)i;
     memcpy(t->prescale, ef_aan_prescale, 64);
+    memcpy(t->zigzag, ef_zigzag, 64);
+    for (int n = 0; n < 64; n++) { t->qdef[n] = ef_default_intra_q[ef_zigzag[n]]; t->qdef[64 + n] = 16; }
     return 0;
 }
 

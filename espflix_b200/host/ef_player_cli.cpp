@@ -1,5 +1,6 @@
-// espflix_b200/host/ef_player_cli.cpp — drives the mirrored MpegDecoder exactly the way the oracle
-// harness drives the reference one (oracle/ref_decode_harness.cpp; espflix.cpp:723-737 decode_next):
+// espflix_b200/host/ef_player_cli.cpp — drives the mirrored MpegDecoder exactly the way the reference's
+// own app drives the original (espflix.cpp:723-737 decode_next; the test harness for the unmodified
+// reference follows the same protocol):
 // pop_empty -> fill Buffer with <= 8 TS packets -> push_full, decoder thread in run(), frames
 // captured from push_video, final flush_picture(1). Usage: ef_player_cli in.ts out.i420 [fields.u16 ntsc]
 #include <stdio.h>

@@ -52,7 +52,7 @@ extern "C" {
 #define EF_FB_STRIDE   528           /* video.h:32: 352 luma + 176 chroma per strip row */
 #define EF_FB_STRIPS   12
 #define EF_STRIP_BYTES 8448          /* 16 rows x 528 */
-#define EF_FRAME_BYTES 101376        /* 12 strips, contiguous on the device */
+#define EF_FRAME_BYTES 101376        /* 12 strips back to back (host layout); the device keeps frames macroblock-tiled */
 #define EF_I420_BYTES  101376
 #define EF_NTSC_FIELD_SAMPLES (262 * 912)
 #define EF_PAL_FIELD_SAMPLES  (312 * 1136)
@@ -102,7 +102,8 @@ int ef_read_frame(ef_ctx* ctx, int stream_index, int fb, uint8_t* dst_strips /* 
 int ef_read_frame_i420(ef_ctx* ctx, int stream_index, int fb, uint8_t* dst /* EF_I420_BYTES */);
 int ef_write_frame_i420(ef_ctx* ctx, int stream_index, int fb, const uint8_t* src);   /* tests / GUI-drawn frames */
 int ef_write_frame(ef_ctx* ctx, int stream_index, int fb, const uint8_t* src_strips /* EF_FRAME_BYTES */);
-/* Device address of a stream's frame store (for zero-copy consumers); fb as above but not -1. */
+/* Device address of a stream's frame store (for zero-copy consumers; macroblock-tiled: tile (mx,my) at
+ * (my*22+mx)*384 = Y[16][16], block-4 chroma [8][8], block-5 chroma [8][8]); fb as above but not -1. */
 int ef_frame_device_ptr(ef_ctx* ctx, int stream_index, int fb, void** ptr);
 /* Batched read-back of the most recent picture of streams [first, first+count) as I420. */
 int ef_read_latest_i420(ef_ctx* ctx, int first, int count, uint8_t* dst, void* stream);
