@@ -202,7 +202,7 @@ def run_gpu(args):
     gen, stream_list = make_streams(streams)
     sizes = np.diff(gen[0][1].astype(np.int64))
     ctx = espflix_b200.Context(n_streams=streams, max_pictures=PICTURES, max_slices_per_picture=12,
-                               es_capacity=sum(len(s) for s in stream_list) + 4096, device=local, fields=False)
+                               es_capacity=sum(len(s) for s in stream_list) + 4096, device=local, fields=True)
     blob_np, off_np = ctx.pack(stream_list)
     es_bytes = int(off_np[-1])
     pinned_es = torch.empty(es_bytes, dtype=torch.uint8, pin_memory=True)
@@ -272,6 +272,25 @@ def run_gpu(args):
     e2e_ms = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - w0))   # host-blocking copies: take the larger of device and wall time
     clocks = sampler.summary() if rank == 0 else None
 
+    # K2: composite field synthesis of the most recent picture of every stream (one launch per field)
+    k2 = {}
+    for ntsc, name, samples in ((1, "ntsc", 262 * 912), (0, "pal", 312 * 1136)):
+        ctx.video_init(ntsc)
+        for fc in range(3):
+            ctx.composite_field(-1, fc, st)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        c0.record()
+        for fc in range(args.steps):
+            ctx.composite_field(-1, fc, st)
+        c1.record()
+        barrier()
+        ms = c0.elapsed_time(c1) / args.steps
+        bytes_per_field = FRAME_BYTES + samples * 2                     # frame read once, whole field written
+        k2[name] = {"fields_per_s": streams / (ms / 1000.0), "ms_per_launch": ms,
+                    "achieved_gbs": streams * bytes_per_field / (ms / 1000.0) / 1e9, "algorithmic_bytes_per_field": bytes_per_field}
+    ctx.video_init(1)
+
     # max over ranks, total frames via one all_gather (reporting only)
     frames_done = streams * PICTURES * args.steps
     if dist is not None:
@@ -310,6 +329,7 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": algo_bytes, "k1_ms_per_step": k1_ms / args.steps,
                          "k1_share_of_step": k1_ms / ms_total},
+            "composite": {k: dict(v, frac=v["achieved_gbs"] / peak) for k, v in k2.items()},
             "per_gpu_frames_per_s": value / world,
             "es_bytes_per_picture": es_bytes / (streams * PICTURES),
             "picture_bytes_first_stream": [int(x) for x in sizes],

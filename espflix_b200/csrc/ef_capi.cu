@@ -21,7 +21,7 @@ __global__ void ef_prefix_kernel(EfDev* Dp);
 __global__ void ef_fill_kernel(EfDev* Dp);
 __global__ void ef_ts_len_kernel(const uint8_t* ts, uint64_t n_packets, uint32_t* out_len);
 __global__ void ef_ts_copy_kernel(const uint8_t* ts, uint64_t n_packets, const uint64_t* out_off, uint8_t* es);
-__global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint64_t* off, const uint64_t* ts_off, int n_streams, uint64_t* es_off);
+__global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint64_t* off, const uint64_t* ts_off, int n_streams, uint64_t* es_off, uint8_t* es);
 size_t ef_decode_smem_bytes();
 cudaError_t ef_decode_configure();
 cudaError_t ef_launch_decode(const EfDev* dev, int pic, int ctas, cudaStream_t stream);
@@ -183,7 +183,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     h.max_seq = cfg->max_pictures;
     int rc;
 #define A(ptr, count) if ((rc = dev_alloc(c, &(ptr), (count))) != EF_OK) { ef_destroy(c); return rc; }
-    A(c->d_es, cfg->es_capacity + 64);
+    A(c->d_es, cfg->es_capacity + 1024);
     A(c->d_es_off, (size_t)n + 1);
     A(h.frames, (size_t)n * 2 * EF_FRAME + 1024);
     A(h.seq, (size_t)n * (h.max_seq + 1));
@@ -210,7 +210,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     if (bad) { ef_destroy(c); return fail(EF_EINVAL, "internal: VLC table %d does not fit its lookup shape", bad); }
     CK(cudaMemcpy(dt, &t, sizeof(t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_default_intra, ef_default_intra_ptr(), 64, cudaMemcpyHostToDevice));
-    CK(cudaMemset(c->d_es, 0, cfg->es_capacity + 64));
+    CK(cudaMemset(c->d_es, 0, cfg->es_capacity + 1024));
     CK(cudaMemset(c->d_es_off, 0, ((size_t)n + 1) * 8));
     CK(cudaMemcpy(c->d, &h, sizeof(h), cudaMemcpyHostToDevice));
     *out = c;
@@ -255,7 +255,7 @@ static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, boo
     const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (!ts) {
         CK(cudaMemcpyAsync(c->d_es, src, total, kind, st));
-        CK(cudaMemsetAsync(c->d_es + total, 0, 64, st));
+        CK(cudaMemsetAsync(c->d_es + total, 0, 256, st));
         CK(cudaMemcpyAsync(c->d_es_off, hoff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));          // hoff is a local
         c->es_bytes = total;
@@ -274,7 +274,7 @@ static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, boo
         if (n_packets) {
             ef_ts_len_kernel<<<(unsigned)((n_packets + 255) / 256), 256, 0, st>>>(c->d_ts, n_packets, c->d_pkt_len);
             CK(cudaGetLastError());
-            ef_ts_scan_kernel<<<1, 1024, 0, st>>>(c->d_pkt_len, n_packets, c->d_pkt_off, c->d_ts_off, n, c->d_es_off);
+            ef_ts_scan_kernel<<<1, 1024, 0, st>>>(c->d_pkt_len, n_packets, c->d_pkt_off, c->d_ts_off, n, c->d_es_off, c->d_es);
             CK(cudaGetLastError());
             ef_ts_copy_kernel<<<(unsigned)((n_packets * 32 + 255) / 256), 256, 0, st>>>(c->d_ts, n_packets, c->d_pkt_off, c->d_es);
             CK(cudaGetLastError());

@@ -36,14 +36,15 @@
 // All VLC tables are indexed by (leading zeros, next 5 bits) so that one CLZ + one shared-memory
 // load decodes a symbol. Entry formats:
 //   dct:  bits 0-4 code length INCLUDING the sign bit (0 = invalid), 5-9 run, 10-15 level. level 0 marks
-//         the specials: length 2 = end of block ('10'), run 1 = escape. Row 0 holds the dct_coeff_next
-//         forms '10' / '11s'; row 12 replaces row 0 for the first coefficient of a block ('1s').  [13][32] u16
+//         the specials: length 2 = end of block ('10'), run 1 = escape. Rows 0-12 = dct_coeff_next context
+//         ('10' / '11s' in row 0, row 12 all invalid for >= 12 leading zeros); rows 13-25 = the same for
+//         the first coefficient of a non-intra block, where row 13 is '1s' = (0,1).           [26][32] u16
 //   mba:  bits 0-3 length, 4-9 value (1..33, 34 stuffing, 35 escape)             [8][32]  u16
 //   mv:   bits 0-3 length (sign included), 4-9 value+16                          [7][32]  u16
 //   cbp:  bits 0-3 length, 4-9 pattern, indexed by the next 9 bits               [512]    u16
 //   ptype:bits 0-2 length, 3-7 macroblock_type flags, indexed by next 6 bits     [64]     u8
 struct EfTables {
-    uint16_t dct[13 * 32];
+    uint16_t dct[26 * 32];
     uint16_t mba[8 * 32];
     uint16_t mv[7 * 32];
     uint16_t cbp[512];

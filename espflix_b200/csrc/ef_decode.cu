@@ -45,7 +45,7 @@ constexpr int kScratchWords = 4 * 72;           // IDCT transpose scratch: 4 blo
 constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes + kScratchWords * 4;
 
 struct SharedTables {                           // same layout as the head of EfTables
-    uint16_t dct[13 * 32];
+    uint16_t dct[26 * 32];
     uint16_t mba[8 * 32];
     uint16_t mv[7 * 32];
     uint16_t cbp[512];
@@ -57,27 +57,28 @@ constexpr int kTableBytes = (sizeof(SharedTables) + 15) & ~15;
 // ---------------------------------------------------------------------------------------------
 // bit reader (FILL_BITS/peek_bits/get_bits, player.cpp:348-352, 495-514): MSB-first. `hi` holds
 // the current 32-bit word, `lo` the next one, `nx` the one after (prefetched), pos = bits of `hi`
-// already consumed. peek() is a single funnel shift.
+// already consumed. peek() is a single funnel shift. Reads run at most 12 bytes past the slice
+// (into the next start code); the ES blob carries 256 bytes of zero padding at its end.
 // ---------------------------------------------------------------------------------------------
 struct BitReader {
-    const uint32_t* p;
-    const uint32_t* end;
+    const uint32_t* words;   // the whole ES blob as aligned 32-bit words (cudaMalloc alignment)
+    uint32_t idx;            // next word to fetch
     uint32_t hi, lo, nx;
     int pos;
 
     __device__ __forceinline__ uint32_t fetch()
     {
-        uint32_t v = 0;
-        if (p < end) v = __byte_perm(__ldg(p), 0, 0x0123);
-        p++;
+        const uint32_t* a = words + idx;
+        const uint32_t v = __byte_perm(__ldg(a), 0, 0x0123);
+        if ((idx & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 32));   // next-but-three sector of this slice
+        idx++;
         return v;
     }
-    __device__ __forceinline__ void init(const uint8_t* base, const uint8_t* stop)
+    __device__ __forceinline__ void init(const uint8_t* blob, uint64_t byte_off)
     {
-        uintptr_t a = (uintptr_t)base;
-        p = (const uint32_t*)(a & ~(uintptr_t)3);
-        end = (const uint32_t*)(((uintptr_t)stop + 3) & ~(uintptr_t)3);
-        pos = (int)(a & 3) * 8;
+        words = (const uint32_t*)blob;
+        idx = (uint32_t)(byte_off >> 2);
+        pos = (int)(byte_off & 3) * 8;
         hi = fetch(); lo = fetch(); nx = fetch();
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }
@@ -99,7 +100,7 @@ struct SliceState {
     BitReader br;
     uint8_t* cur;
     const uint8_t* ref;
-    const uint8_t* qcustom;  // stream's scan-order quantiser tables in HBM when they are not the defaults, else null
+    const uint8_t* qtab;     // scan-order quantiser tables [intra 64 | non-intra 64]: the shared-memory defaults or the stream's own in HBM
     int mbw, mbh;
     int mb_x, mb_y;          // last macroblock handled
     int first;               // next macroblock is the first of the slice (Q6)
@@ -172,12 +173,13 @@ __device__ __forceinline__ int dequant(int level, int intra, int qsq)
 
 __device__ __forceinline__ uint32_t pin4(uint32_t pred, int r0, int r1, int r2, int r3)
 {
-    // PIN(b + s) for four pixels (add_block, player.cpp:1189; _pin clamps to [0,248], Q1)
-    int p0 = min(248, max(0, (int)(pred & 0xFF) + r0));
-    int p1 = min(248, max(0, (int)((pred >> 8) & 0xFF) + r1));
-    int p2 = min(248, max(0, (int)((pred >> 16) & 0xFF) + r2));
-    int p3 = min(248, max(0, (int)(pred >> 24) + r3));
-    return (uint32_t)p0 | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16) | ((uint32_t)p3 << 24);
+    // PIN(b + s) for four pixels (add_block, player.cpp:1189; _pin clamps to [0,248], Q1):
+    // max(min(pred + res, 248), 0) is one DPX instruction per pixel
+    const int p0 = __viaddmin_s32_relu((int)(pred & 0xFF), r0, 248);
+    const int p1 = __viaddmin_s32_relu((int)((pred >> 8) & 0xFF), r1, 248);
+    const int p2 = __viaddmin_s32_relu((int)((pred >> 16) & 0xFF), r2, 248);
+    const int p3 = __viaddmin_s32_relu((int)(pred >> 24), r3, 248);
+    return __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
 }
 
 // (a+b+1)>>1 on four packed bytes (mocomp cases 1 and 2, player.cpp:777-805)
@@ -192,47 +194,61 @@ __device__ __forceinline__ uint32_t avg4x4(uint32_t a, uint32_t b, uint32_t c, u
     return ((e >> 2) & m) | (((o >> 2) & m) << 8);
 }
 
-// Three consecutive aligned words of one pixel row of a plane in the tiled frame, starting at the
-// word that holds pixel x. kLuma: 16-pixel tile rows, else 8-pixel chroma tile rows (plane 0/1).
-// Plain byte semantics of mocomp(); coordinates are clamped into the frame (the reference reads
-// whatever lies there; in-frame vectors never get here).
+// Reference pixels of one lane's 8-pixel segment: three consecutive aligned words of the row that
+// holds pixel (x, y) of a plane in the tiled frame, and of the row below when the vector has a
+// vertical half-pel. kLuma: 16-pixel tile rows, else 8-pixel chroma tile rows (plane 0/1).
+// Loads are issued early (before the IDCT) and consumed late, so their latency hides behind it.
+struct PredWords { uint32_t a0, a1, a2, b0, b1, b2; };
+
 template <bool kLuma>
-__device__ __forceinline__ void row_words(const uint8_t* ref, int plane, int x, int y, uint32_t& w0, uint32_t& w1, uint32_t& w2)
+__device__ __forceinline__ void pred_load(const uint8_t* ref, int plane, int x, int y, bool yh, bool inside, PredWords& w)
 {
     constexpr int W = kLuma ? EF_W : EF_W / 2, H = kLuma ? EF_H : EF_H / 2, TS = kLuma ? 16 : 8, SH = kLuma ? 4 : 3;
-    y = max(0, min(H - 1, y));
-    int xa = max(0, min(W - 4, x & ~3));
-    int xb = min(W - 4, xa + 4), xc = min(W - 4, xa + 8);
-    const int rowbase = (y >> SH) * EF_MBW_MAX * EF_TILE + (kLuma ? 0 : 256 + plane * 64) + (y & (TS - 1)) * TS;
-    w0 = *(const uint32_t*)(ref + rowbase + (xa >> SH) * EF_TILE + (xa & (TS - 1)));
-    w1 = *(const uint32_t*)(ref + rowbase + (xb >> SH) * EF_TILE + (xb & (TS - 1)));
-    w2 = *(const uint32_t*)(ref + rowbase + (xc >> SH) * EF_TILE + (xc & (TS - 1)));
+    const int rowstride = EF_MBW_MAX * EF_TILE;
+    const int plane_off = kLuma ? 0 : 256 + plane * 64;
+    if (inside) {       // whole macroblock prediction lies in the frame (always, for streams the reference accepts)
+        const int xa = x & ~3, xi = xa & (TS - 1);
+        const int o0 = (y >> SH) * rowstride + plane_off + (y & (TS - 1)) * TS + (xa >> SH) * EF_TILE + xi;
+        const int o1 = o0 + (xi + 4 < TS ? 4 : EF_TILE + 4 - TS);
+        const int xj = (xi + 4) & (TS - 1);
+        const int o2 = o1 + (xj + 4 < TS ? 4 : EF_TILE + 4 - TS);
+        w.a0 = *(const uint32_t*)(ref + o0); w.a1 = *(const uint32_t*)(ref + o1); w.a2 = *(const uint32_t*)(ref + o2);
+        if (yh) {
+            const int d = ((y & (TS - 1)) == TS - 1) ? rowstride - (TS - 1) * TS : TS;
+            w.b0 = *(const uint32_t*)(ref + o0 + d); w.b1 = *(const uint32_t*)(ref + o1 + d); w.b2 = *(const uint32_t*)(ref + o2 + d);
+        }
+    } else {            // plain byte semantics of mocomp() with coordinates clamped into the frame (the reference reads whatever lies there)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (r == 1 && !yh) break;
+            const int yy = max(0, min(H - 1, y + r));
+            const int xa = max(0, min(W - 4, x & ~3)), xb = min(W - 4, xa + 4), xc = min(W - 4, xa + 8);
+            const int rowbase = (yy >> SH) * rowstride + plane_off + (yy & (TS - 1)) * TS;
+            const uint32_t v0 = *(const uint32_t*)(ref + rowbase + (xa >> SH) * EF_TILE + (xa & (TS - 1)));
+            const uint32_t v1 = *(const uint32_t*)(ref + rowbase + (xb >> SH) * EF_TILE + (xb & (TS - 1)));
+            const uint32_t v2 = *(const uint32_t*)(ref + rowbase + (xc >> SH) * EF_TILE + (xc & (TS - 1)));
+            if (r == 0) { w.a0 = v0; w.a1 = v1; w.a2 = v2; } else { w.b0 = v0; w.b1 = v1; w.b2 = v2; }
+        }
+    }
 }
 
-// Eight predicted pixels whose first one is pixel (x, y) of the reference plane, with half-pel flags.
-template <bool kLuma>
-__device__ __forceinline__ void predict8(const uint8_t* ref, int plane, int x, int y, int xh, int yh, uint32_t& o0, uint32_t& o1)
+// eight predicted pixels from the loaded words (the four cases of mocomp(), player.cpp:767-820)
+__device__ __forceinline__ void pred_finish(const PredWords& w, int x, int xh, int yh, uint32_t& o0, uint32_t& o1)
 {
     const int sh = (x & 3) * 8;
-    uint32_t w0, w1, w2;
-    row_words<kLuma>(ref, plane, x, y, w0, w1, w2);
-    const uint32_t p0 = __funnelshift_r(w0, w1, sh), p1 = __funnelshift_r(w1, w2, sh);
+    const uint32_t p0 = __funnelshift_r(w.a0, w.a1, sh), p1 = __funnelshift_r(w.a1, w.a2, sh);
     if (xh) {
-        const uint32_t q0 = __funnelshift_rc(w0, w1, sh + 8), q1 = __funnelshift_rc(w1, w2, sh + 8);
+        const uint32_t q0 = __funnelshift_rc(w.a0, w.a1, sh + 8), q1 = __funnelshift_rc(w.a1, w.a2, sh + 8);
         if (yh) {
-            uint32_t v0, v1, v2;
-            row_words<kLuma>(ref, plane, x, y + 1, v0, v1, v2);
-            o0 = avg4x4(p0, q0, __funnelshift_r(v0, v1, sh), __funnelshift_rc(v0, v1, sh + 8));
-            o1 = avg4x4(p1, q1, __funnelshift_r(v1, v2, sh), __funnelshift_rc(v1, v2, sh + 8));
+            o0 = avg4x4(p0, q0, __funnelshift_r(w.b0, w.b1, sh), __funnelshift_rc(w.b0, w.b1, sh + 8));
+            o1 = avg4x4(p1, q1, __funnelshift_r(w.b1, w.b2, sh), __funnelshift_rc(w.b1, w.b2, sh + 8));
         } else {
             o0 = avg2x4(p0, q0);
             o1 = avg2x4(p1, q1);
         }
     } else if (yh) {
-        uint32_t v0, v1, v2;
-        row_words<kLuma>(ref, plane, x, y + 1, v0, v1, v2);
-        o0 = avg2x4(p0, __funnelshift_r(v0, v1, sh));
-        o1 = avg2x4(p1, __funnelshift_r(v1, v2, sh));
+        o0 = avg2x4(p0, __funnelshift_r(w.b0, w.b1, sh));
+        o1 = avg2x4(p1, __funnelshift_r(w.b1, w.b2, sh));
     } else {
         o0 = p0; o1 = p1;
     }
@@ -372,12 +388,12 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     const int rblk = (prow >> 3) * 2 + phalf;       // block that those pixels belong to
     const int rrow = prow & 7;                      // row of that block
     const int crow = lane & 7, cplane = (lane >> 3) & 1;   // chroma row / plane owned by lanes 0..15
-    uint8_t izz[8], psc[8];
+    int izz[8], psc[8];                             // scan position / AAN prescale of the 8 coefficients of column `col`
 #pragma unroll
     for (int r = 0; r < 8; r++) { izz[r] = D.tables->izz[r * 8 + col]; psc[r] = D.tables->prescale[r * 8 + col]; }
 
     SliceState s;
-    s.first = 0; s.cur = nullptr; s.ref = nullptr; s.qcustom = nullptr; s.mbw = 0;
+    s.first = 0; s.cur = nullptr; s.ref = nullptr; s.qtab = T.qdef; s.mbw = 0;
     bool active = false, exhausted = false;
 
     for (;;) {
@@ -398,13 +414,11 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                     const EfSeq* seq = D.seq + (size_t)w.stream * (D.max_seq + 1) + (w.info >> 16);
                     s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
                     s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
-                    s.qcustom = seq->custom ? seq->q_scan : nullptr;
+                    s.qtab = seq->custom ? (const uint8_t*)seq->q_scan : (const uint8_t*)T.qdef;
                     const uint32_t fb = (D.base_pics[w.stream] + (uint32_t)pic + 1u) & 1u;     // flush_picture(), player.cpp:692
                     s.cur = D.frames + ef_frame_offset((int)w.stream, (int)fb);
                     s.ref = D.frames + ef_frame_offset((int)w.stream, (int)(fb ^ 1u));
-                    const uint8_t* es = D.es + D.es_off[w.stream];
-                    const uint8_t* stop = D.es + D.es_off[w.stream + 1];
-                    s.br.init(es + w.es_off, stop);
+                    s.br.init(D.es, D.es_off[w.stream] + w.es_off);
                     s.mb_y = code - 2; s.mb_x = s.mbw - 1;   // slice(), player.cpp:1255: the first increment lands on column 0 of row code-1
                     s.first = 1;
                     s.dc_y = s.dc_cr = s.dc_cb = 128; s.mv_h = s.mv_v = 0;
@@ -428,8 +442,9 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
 
         // ---- phase 1b: flat coefficient state machine, one VLC symbol per lane per step ----------
         int cnt = 0, n1mask = 0, abortmask = 0, blk = 0, n = 0;
+        uint32_t* wptr = list;
         bool busy = have && cbp_rem != 0, start = true;
-        const int qsbase = intra ? 0 : 64;
+        const uint8_t* qrow = s.qtab + (intra ? 0 : 64);
         while (__any_sync(0xFFFFFFFFu, busy)) {
             if (busy) {
                 BitReader& br = s.br;
@@ -441,9 +456,8 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                     start = false;
                 }
                 const uint32_t bits = br.peek();
-                const int lz = __clz(bits);
-                uint32_t e = 0;
-                if (lz <= 11) e = T.dct[((n == 0 && lz == 0) ? 384 : lz * 32) + ((bits << (lz + 1)) >> 27)];
+                const int lz = min(__clz(bits), 12);               // row 12 / 25 = not a code
+                const uint32_t e = T.dct[(n == 0 ? 13 * 32 : 0) + lz * 32 + ((bits << (lz + 1)) >> 27)];
                 int len = e & 31, run = (e >> 5) & 31, level = (int)(e >> 10);
                 bool end_block = false, derail = false;
                 if (level) {
@@ -468,12 +482,11 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                         n += run;
                         if (n >= 64) { abortmask |= 1 << blk; end_block = true; }      // block() returns -1: nothing is stored
                         else {
-                            int q;
-                            if (s.qcustom) q = __ldg(s.qcustom + qsbase + n); else q = T.qdef[qsbase + n];
-                            const int v = dequant(level, intra, s.qscale * q);
+                            const int v = dequant(level, intra, s.qscale * (int)qrow[n]);
                             const uint32_t ent = ((uint32_t)v & 0xFFFFu) | ((uint32_t)n << 16) | ((uint32_t)blk << 22);
-                            if (cnt < kListEntries) list[cnt] = ent; else ovf[cnt - kListEntries] = ent;
-                            cnt++; n++;
+                            *wptr++ = ent;
+                            if (++cnt == kListEntries) wptr = ovf;                 // spill the rest of a very long macroblock to HBM
+                            n++;
                         }
                     }
                     if (end_block) { start = true; busy = cbp_rem != 0; }
@@ -505,6 +518,21 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             const int entries = cntw & 0xFFFF, skip_before = cntw >> 16;
             const int live = cbp & ~abm;
 
+            const int mvh = (int)(int16_t)(mvw & 0xFFFF), mvv = (int)(int16_t)(mvw >> 16);
+            const int tile = ef_tile_offset(mx, my);
+
+            // ---- prediction loads first: 8 luma pixels per lane, 8 chroma pixels for lanes 0..15 ---
+            const int hx = mx * 32 + mvh, hy = my * 32 + mvv;                       // predict(), player.cpp:882
+            const int cx = hx >> 1, cy = hy >> 1;                                   // Q3: floor
+            const int lx = (hx >> 1) + phalf * 8, ly = (hy >> 1) + prow;
+            const int kx = cx >> 1, ky = (cy >> 1) + crow;
+            PredWords wy, wc;
+            if (!intra_r) {
+                const bool inside = hx >= 0 && hy >= 0 && (hx >> 1) + 16 + (hx & 1) <= EF_W && (hy >> 1) + 16 + (hy & 1) <= EF_H;
+                pred_load<true>(ref, 0, lx, ly, hy & 1, inside, wy);
+                if (lane < 16) pred_load<false>(ref, cplane, kx, ky, cy & 1, inside, wc);
+            }
+
             // expand the coefficient list into the dense scratch
             const uint32_t* rl = (const uint32_t*)wbase + r * kListEntries;
             for (int j = lane; j < entries; j += 32) {
@@ -520,20 +548,6 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                     if (sy < 0) break;
                     const int to = ef_tile_offset(sx, sy);
                     if (lane < 24) *(uint4*)(cur + to + lane * 16) = *(const uint4*)(ref + to + lane * 16);
-                }
-            }
-
-            const int mvh = (int)(int16_t)(mvw & 0xFFFF), mvv = (int)(int16_t)(mvw >> 16);
-            const int tile = ef_tile_offset(mx, my);
-
-            // ---- prediction: 8 luma pixels per lane, 8 chroma pixels for lanes 0..15 ------------
-            uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
-            if (!intra_r) {
-                const int hx = mx * 32 + mvh, hy = my * 32 + mvv;
-                predict8<true>(ref, 0, (hx >> 1) + phalf * 8, (hy >> 1) + prow, hx & 1, hy & 1, py0, py1);
-                if (lane < 16) {
-                    const int cx = hx >> 1, cy = hy >> 1;                           // Q3: floor
-                    predict8<false>(ref, cplane, cx >> 1, (cy >> 1) + crow, cx & 1, cy & 1, pc0, pc1);
                 }
             }
             __syncwarp();                                                           // dense[] complete
@@ -555,8 +569,9 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
 #pragma unroll
                 for (int i = 0; i < 8; i++) v[i] = 0;
                 if (full) {
+                    const int16_t* db = dense + bk * 64;
 #pragma unroll
-                    for (int rr = 0; rr < 8; rr++) v[rr] = (int)dense[bk * 64 + izz[rr]] * (int)psc[rr];     // b[zz] = v * scale_dct_q[zz]
+                    for (int rr = 0; rr < 8; rr++) v[rr] = (int)db[izz[rr]] * psc[rr];       // b[zz] = v * scale_dct_q[zz]
                     if (intra_r && col == 0) v[0] = (int)((uint32_t)dcs[bk] << 8);      // b[0] <<= 8, player.cpp:1065
                     idct8<false>(v);
                 }
@@ -594,7 +609,12 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                 }
             }
 
-            // ---- combine + store (copy_block / copy_block_dc / add_block / add_block_dc) --------
+            // ---- finish the prediction, combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
+            uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
+            if (!intra_r) {
+                pred_finish(wy, lx, hx & 1, hy & 1, py0, py1);
+                if (lane < 16) pred_finish(wc, kx, cx & 1, cy & 1, pc0, pc1);
+            }
             {
                 const bool coded = (cbp >> rblk) & 1, aborted = (abm >> rblk) & 1, n1 = (n1m >> rblk) & 1;
                 uint32_t o0 = py0, o1 = py1;

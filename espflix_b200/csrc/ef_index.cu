@@ -283,7 +283,7 @@ __global__ void ef_ts_copy_kernel(const uint8_t* __restrict__ ts, uint64_t n_pac
 // exclusive scan of u32 lengths into u64 offsets, plus per-stream ES offsets: single CTA, sequential over chunks
 __global__ void __launch_bounds__(1024)
 ef_ts_scan_kernel(const uint32_t* __restrict__ len, uint64_t n_packets, uint64_t* __restrict__ off,
-                  const uint64_t* __restrict__ ts_off, int n_streams, uint64_t* __restrict__ es_off)
+                  const uint64_t* __restrict__ ts_off, int n_streams, uint64_t* __restrict__ es_off, uint8_t* __restrict__ es)
 {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t carry;
@@ -311,6 +311,8 @@ ef_ts_scan_kernel(const uint32_t* __restrict__ len, uint64_t n_packets, uint64_t
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
+    // K1's bit reader runs a few bytes past the last slice: zero the 256 bytes behind the elementary stream
+    if (threadIdx.x < 256) es[carry + threadIdx.x] = 0;
     // stream boundaries: ES offset of stream s = offset of its first packet
     for (int s = threadIdx.x; s <= n_streams; s += 1024) {
         const uint64_t pk = ts_off[s] / 188;

@@ -46,7 +46,8 @@ int ef_build_tables(EfTables* t)
     }
     if (!place(t->dct, 12, "10", (uint16_t)2)) return 1;               // end of block: level 0, length 2
     if (!place(t->dct, 12, "000001", (uint16_t)(6 | (1 << 5)))) return 1;   // escape: level 0, run 1
-    for (int i = 0; i < 32; i++) t->dct[12 * 32 + i] = (uint16_t)(2 | (0 << 5) | (1 << 10));   // first coefficient: "1s" = (0,1)
+    memcpy(t->dct + 13 * 32, t->dct, 13 * 32 * sizeof(uint16_t));      // first-coefficient context = same table ...
+    for (int i = 0; i < 32; i++) t->dct[13 * 32 + i] = (uint16_t)(2 | (0 << 5) | (1 << 10));   // ... except "1s" = (0,1) instead of "10"/"11s"
     for (int i = 0; i < EF_VLC_MBA_COUNT; i++) {
         int len = (int)strlen(ef_vlc_mba[i].code);
         if (!place(t->mba, 8, ef_vlc_mba[i].code, (uint16_t)(len | (ef_vlc_mba[i].value << 4)))) return 2;
