@@ -50,6 +50,7 @@ struct EfTables {
     uint16_t cbp[512];
     uint8_t ptype[64];
     uint8_t qdef[128];      // default quantiser matrices in SCAN order: [0..63] intra, [64..127] non-intra (all 16)
+    uint16_t zp[64];        // scan position n -> zig_zag[n] | scale_dct_q[zig_zag[n]] << 8 (player.cpp:150-170)
     uint8_t izz[64];        // raster index -> zig-zag scan position
     uint8_t prescale[64];   // AAN prescale, raster (reference scale_dct_q, player.cpp:161)
     uint8_t zigzag[64];     // scan position -> raster index

@@ -15,7 +15,8 @@
 //     (block, scan position, value) entry to the lane's list in shared memory (96 entries; the rare
 //     longer macroblock spills to a per-lane HBM area).
 //   * then the whole WARP reconstructs the 32 macroblocks one after another: scatter the list into
-//     a dense 6x64 scratch, the reference's integer AAN IDCT with one lane per block column / row
+//     a dense 6x64 scratch (values already de-zigzagged and AAN-prescaled by the parser), the
+//     reference's integer AAN IDCT in place with one lane per block column, then per block row
 //     (4 luma blocks = 32 lanes), half-pel motion compensation and the clamped add with one lane
 //     per 8-pixel row segment.
 //   * frame stores are MACROBLOCK-TILED in HBM (ef_common.cuh): a macroblock is 384 contiguous
@@ -40,9 +41,9 @@ constexpr int kHdrInfo = 24;                    // bit0 valid, 1 intra, 2-7 code
 constexpr int kHdrCnt = 28;                     // list entries | skip_before << 16
 constexpr int kHdrMv = 32;                      // (int16 h) | (int16 v) << 16, half-pel units
 constexpr int kHdrBytes = 32 * kHdrStride;
-constexpr int kDenseBytes = 6 * 64 * 2;         // int16 [6][64] dequantised coefficients, scan order
-constexpr int kScratchWords = 4 * 72;           // IDCT transpose scratch: 4 blocks x (64 + 8 pad) ints
-constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes + kScratchWords * 4;
+constexpr int kDenseStride = 72;                // words per block in the dense scratch: 64 + 8 pad -> the 4 luma blocks hit distinct banks
+constexpr int kDenseBytes = 6 * kDenseStride * 4;   // int32 [6][72] prescaled coefficients, raster order; also the IDCT transpose buffer
+constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes;
 
 struct SharedTables {                           // same layout as the head of EfTables
     uint16_t dct[26 * 32];
@@ -51,6 +52,7 @@ struct SharedTables {                           // same layout as the head of Ef
     uint16_t cbp[512];
     uint8_t ptype[64];
     uint8_t qdef[128];
+    uint16_t zp[64];                            // scan position -> raster index | AAN prescale << 8
 };
 constexpr int kTableBytes = (sizeof(SharedTables) + 15) & ~15;
 
@@ -371,8 +373,7 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     uint8_t* wbase = smem + kTableBytes + (size_t)warp * kWarpBytes;
     uint32_t* list = (uint32_t*)wbase + lane * kListEntries;
     uint8_t* hdr = wbase + kListBytes + lane * kHdrStride;
-    int16_t* dense = (int16_t*)(wbase + kListBytes + kHdrBytes);
-    int* scratch = (int*)(wbase + kListBytes + kHdrBytes + kDenseBytes);
+    int* dense = (int*)(wbase + kListBytes + kHdrBytes);
     uint32_t* ovf = D.k1_overflow + ((size_t)(blockIdx.x * kWarpsPerCta + warp) * 32 + lane) * (384 - kListEntries);
     for (int i = lane; i < kDenseBytes / 4; i += 32) ((uint32_t*)dense)[i] = 0;
     __syncthreads();
@@ -388,9 +389,6 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     const int rblk = (prow >> 3) * 2 + phalf;       // block that those pixels belong to
     const int rrow = prow & 7;                      // row of that block
     const int crow = lane & 7, cplane = (lane >> 3) & 1;   // chroma row / plane owned by lanes 0..15
-    int izz[8], psc[8];                             // scan position / AAN prescale of the 8 coefficients of column `col`
-#pragma unroll
-    for (int r = 0; r < 8; r++) { izz[r] = D.tables->izz[r * 8 + col]; psc[r] = D.tables->prescale[r * 8 + col]; }
 
     SliceState s;
     s.first = 0; s.cur = nullptr; s.ref = nullptr; s.qtab = T.qdef; s.mbw = 0;
@@ -483,7 +481,8 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                         if (n >= 64) { abortmask |= 1 << blk; end_block = true; }      // block() returns -1: nothing is stored
                         else {
                             const int v = dequant(level, intra, s.qscale * (int)qrow[n]);
-                            const uint32_t ent = ((uint32_t)v & 0xFFFFu) | ((uint32_t)n << 16) | ((uint32_t)blk << 22);
+                            const uint32_t zp = T.zp[n];                                   // zz = zig_zag[n]; b[zz] = v * scale_dct_q[zz] (player.cpp:1108, 1121)
+                            const uint32_t ent = ((uint32_t)(v * (int)(zp >> 8)) & 0x3FFFFu) | ((zp & 63u) << 18) | ((uint32_t)blk << 24);
                             *wptr++ = ent;
                             if (++cnt == kListEntries) wptr = ovf;                 // spill the rest of a very long macroblock to HBM
                             n++;
@@ -537,7 +536,8 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             const uint32_t* rl = (const uint32_t*)wbase + r * kListEntries;
             for (int j = lane; j < entries; j += 32) {
                 const uint32_t ent = j < kListEntries ? rl[j] : rovf[j - kListEntries];
-                dense[((ent >> 22) & 7) * 64 + ((ent >> 16) & 63)] = (int16_t)(ent & 0xFFFF);
+                const int eb = (ent >> 24) & 7;
+                if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((ent >> 18) & 63)] = ((int)(ent << 14)) >> 14;   // 18-bit signed value
             }
 
             // skipped macroblocks: predict_zero() copies them from the reference frame (player.cpp:1283-1288)
@@ -564,41 +564,38 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                 if (!(live & setmask)) continue;                         // warp-uniform
                 const int bk = set == 0 ? cblk : 4 + (cblk & 1);
                 const bool lane_on = set == 0 || lane < 16;
-                const bool full = lane_on && ((live & ~n1m) >> bk) & 1;
-                int v[8];
+                // column pass, in place: lane (block, column) owns the 8 words dense[block][0..7][column]
+                if (lane_on) {
+                    int* db = dense + bk * kDenseStride + col;
+                    int v[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = 0;
-                if (full) {
-                    const int16_t* db = dense + bk * 64;
-#pragma unroll
-                    for (int rr = 0; rr < 8; rr++) v[rr] = (int)db[izz[rr]] * psc[rr];       // b[zz] = v * scale_dct_q[zz]
+                    for (int rr = 0; rr < 8; rr++) v[rr] = db[rr * 8];
                     if (intra_r && col == 0) v[0] = (int)((uint32_t)dcs[bk] << 8);      // b[0] <<= 8, player.cpp:1065
                     idct8<false>(v);
-                }
-                int* Tb = scratch + cblk * 72;
-                if (lane_on) {
 #pragma unroll
-                    for (int rr = 0; rr < 8; rr++) Tb[rr * 8 + col] = v[rr];
+                    for (int rr = 0; rr < 8; rr++) db[rr * 8] = v[rr];
                 }
                 __syncwarp();
                 // row pass: luma lanes own (rblk, rrow); chroma lanes 0..15 own (4 + lane/8, lane%8)
-                const int ob = set == 0 ? rblk : cplane;                  // scratch slot of the row this lane owns
                 const int orow = set == 0 ? rrow : crow;
                 const int oblk = set == 0 ? rblk : 4 + cplane;
                 const bool ocoded = lane_on && (live >> oblk) & 1;
-                const bool ofull = ocoded && !((n1m >> oblk) & 1);
                 int w[8];
-                {
-                    const int4 a = *(const int4*)(scratch + ob * 72 + orow * 8);
-                    const int4 b = *(const int4*)(scratch + ob * 72 + orow * 8 + 4);
+#pragma unroll
+                for (int i = 0; i < 8; i++) w[i] = 0;
+                if (lane_on) {
+                    int4* rowp = (int4*)(dense + oblk * kDenseStride + orow * 8);
+                    const int4 a = rowp[0], b = rowp[1];
+                    rowp[0] = make_int4(0, 0, 0, 0); rowp[1] = make_int4(0, 0, 0, 0);    // leave the scratch zeroed for the next macroblock
                     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
                 }
-                __syncwarp();
-                if (ofull) idct8<true>(w);
-                else if (ocoded) {                                       // n == 1: dc = b[0] >> 8 (Q5); scale_dct_q[0] = 32
-                    const int dc = intra_r ? dcs[oblk] : ((int)dense[oblk * 64] * 32) >> 8;
+                if (ocoded) {
+                    if (!((n1m >> oblk) & 1)) idct8<true>(w);
+                    else {                                               // n == 1: dc = b[0] >> 8 (Q5); after the column pass every row holds b[0] in column 0
+                        const int dc = intra_r ? dcs[oblk] : w[0] >> 8;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) w[i] = dc;
+                        for (int i = 0; i < 8; i++) w[i] = dc;
+                    }
                 }
                 if (set == 0) {
 #pragma unroll
@@ -607,6 +604,7 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
 #pragma unroll
                     for (int i = 0; i < 8; i++) resC[i] = w[i];
                 }
+                __syncwarp();
             }
 
             // ---- finish the prediction, combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
@@ -647,11 +645,6 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                 if (store) *(uint2*)(cur + tile + 256 + cplane * 64 + crow * 8) = make_uint2(o0, o1);
             }
 
-            // ---- clear the dense slots this macroblock used --------------------------------------
-            for (int j = lane; j < entries; j += 32) {
-                const uint32_t ent = j < kListEntries ? rl[j] : rovf[j - kListEntries];
-                dense[((ent >> 22) & 7) * 64 + ((ent >> 16) & 63)] = 0;
-            }
             __syncwarp();
         }
     }

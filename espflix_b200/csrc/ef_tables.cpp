@@ -82,6 +82,7 @@ int ef_build_tables(EfTables* t)
     memcpy(t->prescale, ef_aan_prescale, 64);
     memcpy(t->zigzag, ef_zigzag, 64);
     for (int n = 0; n < 64; n++) { t->qdef[n] = ef_default_intra_q[ef_zigzag[n]]; t->qdef[64 + n] = 16; }
+    for (int n = 0; n < 64; n++) t->zp[n] = (uint16_t)(ef_zigzag[n] | (ef_aan_prescale[ef_zigzag[n]] << 8));
     return 0;
 }
 
