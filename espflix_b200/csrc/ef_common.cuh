@@ -29,8 +29,8 @@
 #define EF_MBW_MAX 22
 #define EF_MBH_MAX 12
 #define EF_TILE 384          // bytes per macroblock tile: 256 Y + 64 + 64 chroma
-#define EF_K1_WARPS 14       // warps per K1 CTA (one CTA per SM; shared-memory bound)
-#define EF_K1_LIST 96        // per-lane coefficient list entries kept in shared memory (rest spills to HBM)
+#define EF_K1_WARPS 15       // warps per K1 CTA (one CTA per SM; shared-memory bound)
+#define EF_K1_LIST 80        // per-lane coefficient list entries kept in shared memory (rest spills to HBM)
 
 // ---- decode tables (built on the host by ef_tables.cpp from ISO 11172-2 Annex B) -------------
 // All VLC tables are indexed by (leading zeros, next 5 bits) so that one CLZ + one shared-memory

@@ -16,29 +16,41 @@ namespace {
 
 __device__ __forceinline__ uint32_t chroma_word(const uint32_t* tab, uint32_t u, uint32_t v, int vt)
 {
-    return ((tab[u & 255] + tab[vt + (v & 255)]) & 0xFCFCFCFCu) >> 2;      // CHROMA_EVEN / CHROMA_ODD, video.cpp:670
+    return ((__ldg(tab + (u & 255)) + __ldg(tab + vt + (v & 255))) & 0xFCFCFCFCu) >> 2;      // CHROMA_EVEN / CHROMA_ODD, video.cpp:670
 }
 
-__device__ __forceinline__ uint16_t blank_sample(const EfGeometry& g, const int16_t* pal_burst, int line, int x)
+// compile-time geometry of the two standards (video_init / pal_init, video.cpp:572-630; values
+// probe-verified against the reference in tests/golden/composite_pins.json)
+template <bool kNtsc> struct Geo;
+template <> struct Geo<true> {
+    static constexpr int W = 912, LINES = 262, HSYNC = 64, HSYNC_LONG = 840, HSYNC_SHORT = 0, BURST_START = 64, BURST_W = 40,
+                         TOP = 32, VSYNC = 259, BLIT = 160;
+};
+template <> struct Geo<false> {
+    static constexpr int W = 1136, LINES = 312, HSYNC = 80, HSYNC_LONG = 536, HSYNC_SHORT = 32, BURST_START = 96, BURST_W = 44,
+                         TOP = 64, VSYNC = 304, BLIT = 280;
+};
+
+template <bool kNtsc>
+__device__ __forceinline__ uint32_t blank_sample(const int16_t* pal_burst, int line, int x)
 {
-    const uint16_t SYNC = 0x0000, BLANKING = 0x1400, BLACK = 0x1800;       // IRE(-40), IRE(0), IRE(7.5): video.cpp:520-525
-    if (line >= g.vsync_start) {
-        if (g.ntsc) return x < g.hsync_long ? SYNC : BLANKING;             // blanking(buf, true)
+    using G = Geo<kNtsc>;
+    const uint32_t SYNC = 0x0000, BLANKING = 0x1400, BLACK = 0x1800;       // IRE(-40), IRE(0), IRE(7.5): video.cpp:520-525
+    if (line >= G::VSYNC) {
+        if (kNtsc) return x < G::HSYNC_LONG ? SYNC : BLANKING;             // blanking(buf, true)
         const uint32_t types = 0x00233000u;                                // _sync_type[8] = {0,0,0,3,3,2,0,0}, one nibble each
-        const int t = (types >> ((line - g.vsync_start) * 4)) & 15;
-        const int half = g.line_width >> 1;
+        const int t = (types >> ((line - G::VSYNC) * 4)) & 15;
+        const int half = G::W >> 1;
         const int second = x >= half;
         const int xx = second ? x - half : x;
         const int lng = second ? (t & 1) : (t & 2);
-        return xx < (lng ? g.hsync_long : g.hsync_short) ? SYNC : BLANKING; // pal_sync2
+        return xx < (lng ? G::HSYNC_LONG : G::HSYNC_SHORT) ? SYNC : BLANKING; // pal_sync2
     }
-    if (x < g.hsync) return SYNC;
-    if (g.ntsc) {
-        const int i = x - g.hsync;                                         // burst(), video.cpp:806: 10 cycles of [1E00 1400 0A00 1400]
-        if (i < 40) return (i & 1) ? BLANKING : ((i & 2) ? 0x0A00 : 0x1E00);
-    } else {
-        const int i = x - g.burst_start;                                   // burst_pal(): pair-swapped copy, table chosen by (_line_counter after ++) & 1
-        if (i >= 0 && i < g.burst_width) return (uint16_t)pal_burst[(((line + 1) & 1) ? 0 : 64) + (i ^ 1)];
+    if (x < G::HSYNC) return SYNC;
+    const int i = x - G::BURST_START;
+    if (i >= 0 && i < G::BURST_W) {
+        if (kNtsc) return (i & 1) ? BLANKING : ((i & 2) ? 0x0A00u : 0x1E00u);   // burst(), video.cpp:806: 10 cycles of [1E00 1400 0A00 1400]
+        return (uint16_t)pal_burst[(((line + 1) & 1) ? 0 : 64) + (i ^ 1)];     // burst_pal(): pair-swapped, table chosen by (_line_counter after ++) & 1
     }
     return BLACK;
 }
@@ -48,33 +60,29 @@ __constant__ uint32_t c_dither[8] = {                                     // dit
 
 }  // namespace
 
+// grid: x = 16-byte chunks of one field / 256, y = stream
+template <bool kNtsc>
 __global__ void __launch_bounds__(256)
 ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
 {
-    __shared__ uint32_t tab[768];
+    using G = Geo<kNtsc>;
+    constexpr int CPL = G::W / 8;                                          // 16-byte chunks per line
     const EfDev& D = *Dp;
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) tab[i] = D.color_tab[i];
-    __syncthreads();
-
-    const EfGeometry g = D.geo;
-    const int cpl = g.line_width >> 3;                                     // 16-byte chunks per line
-    const uint32_t chunks = (uint32_t)(cpl * g.line_count);
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t stream = (uint32_t)(gid / chunks);
-    const uint32_t c = (uint32_t)(gid % chunks);
-    if (stream >= (uint32_t)D.n_streams) return;
-
-    const int line = (int)(c / (uint32_t)cpl), k = (int)(c % (uint32_t)cpl);
+    const uint32_t* tab = D.color_tab;                                     // 3 KB LUT: lives in L1 through the read-only path
+    const uint32_t c = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t stream = blockIdx.y;
+    if (c >= (uint32_t)(CPL * G::LINES)) return;
+    const int line = (int)(c / CPL), k = (int)(c - (uint32_t)line * CPL);
     const int x0 = k * 8;
-    uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)line * g.line_width + x0;
+    uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)c * 8;
 
-    const int fl = line - g.active_top;                                    // frame line 0..191 on active lines
-    const bool active = fl >= 0 && fl < EF_H && fb_sel != -2;      // -2: no frame presented yet (video.cpp:1140)
+    const int fl = line - G::TOP;                                          // frame line 0..191 on active lines
+    const bool active = fl >= 0 && fl < EF_H && fb_sel != -2;              // -2: no frame presented yet (video.cpp:1140)
     uint32_t w[4];
-    if (active && x0 >= g.blit_start && x0 < g.blit_start + 2 * EF_W) {
+    if (active && x0 >= G::BLIT && x0 < G::BLIT + 2 * EF_W) {
         const int fb = fb_sel >= 0 ? fb_sel : (int)((D.base_pics[stream] + D.n_pics[stream]) & 1u);
         const uint8_t* f = D.frames + ef_frame_offset((int)stream, fb);
-        const int q = (x0 - g.blit_start) >> 3;                            // 4-pixel group index 0..87
+        const int q = (x0 - G::BLIT) >> 3;                                 // 4-pixel group index 0..87
         const uint32_t dither = c_dither[(fl & 3) + ((frame_counter & 1) << 2)];
         // tiled frame (ef_common.cuh): 4 luma pixels of group q sit in tile q>>2, the 2 chroma samples too
         const int cy = fl >> 1;
@@ -108,13 +116,10 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
         // blank and vsync lines, and the part of an active line outside the blit span (which still
         // shows what blanking() last left in the ping-pong buffer: sync, burst, BLACK)
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint16_t a = blank_sample(g, D.pal_burst, line, x0 + 2 * i);
-            const uint16_t b = blank_sample(g, D.pal_burst, line, x0 + 2 * i + 1);
-            w[i] = (uint32_t)a | ((uint32_t)b << 16);
-        }
+        for (int i = 0; i < 4; i++)
+            w[i] = blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i) | (blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i + 1) << 16);
     }
-    *(uint4*)out = make_uint4(w[0], w[1], w[2], w[3]);
+    __stcs((uint4*)out, make_uint4(w[0], w[1], w[2], w[3]));               // streaming store: the field is not re-read by this kernel
 }
 
 // single blit() call into a device buffer (line-blit entry point; used by ef_blit): one thread per 4 luma pixels
@@ -160,9 +165,10 @@ __global__ void ef_blit_kernel(const EfDev* __restrict__ Dp, int stream, int fb,
 
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, cudaStream_t stream)
 {
-    const uint64_t chunks = (uint64_t)(g.line_width >> 3) * g.line_count * (uint64_t)n_streams;
-    const uint64_t blocks = (chunks + 255) / 256;
-    ef_composite_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dev, fb, frame_counter);
+    const unsigned chunks = (unsigned)(g.line_width >> 3) * (unsigned)g.line_count;
+    const dim3 grid((chunks + 255) / 256, (unsigned)n_streams);
+    if (g.ntsc) ef_composite_kernel<true><<<grid, 256, 0, stream>>>(dev, fb, frame_counter);
+    else ef_composite_kernel<false><<<grid, 256, 0, stream>>>(dev, fb, frame_counter);
     return cudaGetLastError();
 }
 

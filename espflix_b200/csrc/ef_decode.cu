@@ -43,7 +43,8 @@ constexpr int kHdrMv = 32;                      // (int16 h) | (int16 v) << 16, 
 constexpr int kHdrBytes = 32 * kHdrStride;
 constexpr int kDenseStride = 72;                // words per block in the dense scratch: 64 + 8 pad -> the 4 luma blocks hit distinct banks
 constexpr int kDenseBytes = 6 * kDenseStride * 4;   // int32 [6][72] prescaled coefficients, raster order; also the IDCT transpose buffer
-constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes;
+constexpr int kStageBytes = 12 * 32 * 4;        // motion-compensation staging: 6 luma + 6 chroma words per lane, word-major
+constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes + kStageBytes;
 
 struct SharedTables {                           // same layout as the head of EfTables
     uint16_t dct[26 * 32];
@@ -65,14 +66,14 @@ constexpr int kTableBytes = (sizeof(SharedTables) + 15) & ~15;
 struct BitReader {
     const uint32_t* words;   // the whole ES blob as aligned 32-bit words (cudaMalloc alignment)
     uint32_t idx;            // next word to fetch
-    uint32_t hi, lo, nx;
+    uint32_t hi, lo, nx_raw; // nx_raw: the prefetched word, still little-endian, so that its load is not waited for until the next refill
     int pos;
 
-    __device__ __forceinline__ uint32_t fetch()
+    __device__ __forceinline__ uint32_t fetch_raw()
     {
         const uint32_t* a = words + idx;
-        const uint32_t v = __byte_perm(__ldg(a), 0, 0x0123);
-        if ((idx & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 32));   // next-but-three sector of this slice
+        const uint32_t v = __ldg(a);
+        if ((idx & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 32));   // 128 bytes ahead of this slice's read position
         idx++;
         return v;
     }
@@ -81,13 +82,13 @@ struct BitReader {
         words = (const uint32_t*)blob;
         idx = (uint32_t)(byte_off >> 2);
         pos = (int)(byte_off & 3) * 8;
-        hi = fetch(); lo = fetch(); nx = fetch();
+        hi = __byte_perm(fetch_raw(), 0, 0x0123); lo = __byte_perm(fetch_raw(), 0, 0x0123); nx_raw = fetch_raw();
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }
     __device__ __forceinline__ void skip(int n)
     {
         pos += n;
-        if (pos >= 32) { pos -= 32; hi = lo; lo = nx; nx = fetch(); }
+        if (pos >= 32) { pos -= 32; hi = lo; lo = __byte_perm(nx_raw, 0, 0x0123); nx_raw = fetch_raw(); }
     }
     __device__ __forceinline__ uint32_t get(int n)     // 1 <= n <= 32
     {
@@ -202,8 +203,16 @@ __device__ __forceinline__ uint32_t avg4x4(uint32_t a, uint32_t b, uint32_t c, u
 // Loads are issued early (before the IDCT) and consumed late, so their latency hides behind it.
 struct PredWords { uint32_t a0, a1, a2, b0, b1, b2; };
 
+// 4-byte asynchronous global->shared copy (LDGSTS): no register, no scoreboard slot, completion via wait_group
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const void* gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+}
+
+// st = this lane's column of the per-warp staging area: word k lives at st[k * 32]
 template <bool kLuma>
-__device__ __forceinline__ void pred_load(const uint8_t* ref, int plane, int x, int y, bool yh, bool inside, PredWords& w)
+__device__ __forceinline__ void pred_load(const uint8_t* ref, int plane, int x, int y, bool yh, bool inside, uint32_t* st)
 {
     constexpr int W = kLuma ? EF_W : EF_W / 2, H = kLuma ? EF_H : EF_H / 2, TS = kLuma ? 16 : 8, SH = kLuma ? 4 : 3;
     const int rowstride = EF_MBW_MAX * EF_TILE;
@@ -214,10 +223,10 @@ __device__ __forceinline__ void pred_load(const uint8_t* ref, int plane, int x, 
         const int o1 = o0 + (xi + 4 < TS ? 4 : EF_TILE + 4 - TS);
         const int xj = (xi + 4) & (TS - 1);
         const int o2 = o1 + (xj + 4 < TS ? 4 : EF_TILE + 4 - TS);
-        w.a0 = *(const uint32_t*)(ref + o0); w.a1 = *(const uint32_t*)(ref + o1); w.a2 = *(const uint32_t*)(ref + o2);
+        cp_async4(st, ref + o0); cp_async4(st + 32, ref + o1); cp_async4(st + 64, ref + o2);
         if (yh) {
             const int d = ((y & (TS - 1)) == TS - 1) ? rowstride - (TS - 1) * TS : TS;
-            w.b0 = *(const uint32_t*)(ref + o0 + d); w.b1 = *(const uint32_t*)(ref + o1 + d); w.b2 = *(const uint32_t*)(ref + o2 + d);
+            cp_async4(st + 96, ref + o0 + d); cp_async4(st + 128, ref + o1 + d); cp_async4(st + 160, ref + o2 + d);
         }
     } else {            // plain byte semantics of mocomp() with coordinates clamped into the frame (the reference reads whatever lies there)
 #pragma unroll
@@ -226,17 +235,19 @@ __device__ __forceinline__ void pred_load(const uint8_t* ref, int plane, int x, 
             const int yy = max(0, min(H - 1, y + r));
             const int xa = max(0, min(W - 4, x & ~3)), xb = min(W - 4, xa + 4), xc = min(W - 4, xa + 8);
             const int rowbase = (yy >> SH) * rowstride + plane_off + (yy & (TS - 1)) * TS;
-            const uint32_t v0 = *(const uint32_t*)(ref + rowbase + (xa >> SH) * EF_TILE + (xa & (TS - 1)));
-            const uint32_t v1 = *(const uint32_t*)(ref + rowbase + (xb >> SH) * EF_TILE + (xb & (TS - 1)));
-            const uint32_t v2 = *(const uint32_t*)(ref + rowbase + (xc >> SH) * EF_TILE + (xc & (TS - 1)));
-            if (r == 0) { w.a0 = v0; w.a1 = v1; w.a2 = v2; } else { w.b0 = v0; w.b1 = v1; w.b2 = v2; }
+            cp_async4(st + r * 96, ref + rowbase + (xa >> SH) * EF_TILE + (xa & (TS - 1)));
+            cp_async4(st + r * 96 + 32, ref + rowbase + (xb >> SH) * EF_TILE + (xb & (TS - 1)));
+            cp_async4(st + r * 96 + 64, ref + rowbase + (xc >> SH) * EF_TILE + (xc & (TS - 1)));
         }
     }
 }
 
 // eight predicted pixels from the loaded words (the four cases of mocomp(), player.cpp:767-820)
-__device__ __forceinline__ void pred_finish(const PredWords& w, int x, int xh, int yh, uint32_t& o0, uint32_t& o1)
+__device__ __forceinline__ void pred_finish(const uint32_t* st, int x, int xh, int yh, uint32_t& o0, uint32_t& o1)
 {
+    PredWords w;
+    w.a0 = st[0]; w.a1 = st[32]; w.a2 = st[64];
+    if (yh) { w.b0 = st[96]; w.b1 = st[128]; w.b2 = st[160]; }
     const int sh = (x & 3) * 8;
     const uint32_t p0 = __funnelshift_r(w.a0, w.a1, sh), p1 = __funnelshift_r(w.a1, w.a2, sh);
     if (xh) {
@@ -374,6 +385,7 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     uint32_t* list = (uint32_t*)wbase + lane * kListEntries;
     uint8_t* hdr = wbase + kListBytes + lane * kHdrStride;
     int* dense = (int*)(wbase + kListBytes + kHdrBytes);
+    uint32_t* stage = (uint32_t*)(wbase + kListBytes + kHdrBytes + kDenseBytes) + lane;
     uint32_t* ovf = D.k1_overflow + ((size_t)(blockIdx.x * kWarpsPerCta + warp) * 32 + lane) * (384 - kListEntries);
     for (int i = lane; i < kDenseBytes / 4; i += 32) ((uint32_t*)dense)[i] = 0;
     __syncthreads();
@@ -525,11 +537,11 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             const int cx = hx >> 1, cy = hy >> 1;                                   // Q3: floor
             const int lx = (hx >> 1) + phalf * 8, ly = (hy >> 1) + prow;
             const int kx = cx >> 1, ky = (cy >> 1) + crow;
-            PredWords wy, wc;
             if (!intra_r) {
                 const bool inside = hx >= 0 && hy >= 0 && (hx >> 1) + 16 + (hx & 1) <= EF_W && (hy >> 1) + 16 + (hy & 1) <= EF_H;
-                pred_load<true>(ref, 0, lx, ly, hy & 1, inside, wy);
-                if (lane < 16) pred_load<false>(ref, cplane, kx, ky, cy & 1, inside, wc);
+                pred_load<true>(ref, 0, lx, ly, hy & 1, inside, stage);
+                if (lane < 16) pred_load<false>(ref, cplane, kx, ky, cy & 1, inside, stage + 192);
+                asm volatile("cp.async.commit_group;");
             }
 
             // expand the coefficient list into the dense scratch
@@ -610,8 +622,9 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             // ---- finish the prediction, combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
             uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
             if (!intra_r) {
-                pred_finish(wy, lx, hx & 1, hy & 1, py0, py1);
-                if (lane < 16) pred_finish(wc, kx, cx & 1, cy & 1, pc0, pc1);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                pred_finish(stage, lx, hx & 1, hy & 1, py0, py1);
+                if (lane < 16) pred_finish(stage + 192, kx, cx & 1, cy & 1, pc0, pc1);
             }
             {
                 const bool coded = (cbp >> rblk) & 1, aborted = (abm >> rblk) & 1, n1 = (n1m >> rblk) & 1;
