@@ -43,8 +43,8 @@ constexpr int kHdrMv = 32;                      // (int16 h) | (int16 v) << 16, 
 constexpr int kHdrBytes = 32 * kHdrStride;
 constexpr int kDenseStride = 72;                // words per block in the dense scratch: 64 + 8 pad -> the 4 luma blocks hit distinct banks
 constexpr int kDenseBytes = 6 * kDenseStride * 4;   // int32 [6][72] prescaled coefficients, raster order; also the IDCT transpose buffer
-constexpr int kStageBytes = 12 * 32 * 4;        // motion-compensation staging: 6 luma + 6 chroma words per lane, word-major
-constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes + kStageBytes;
+constexpr int kStageBytes = 4 * EF_TILE;        // motion-compensation staging: up to 2 x 2 reference tiles per macroblock
+constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes + kStageBytes + 16;   // + the warp's mbarrier
 
 struct SharedTables {                           // same layout as the head of EfTables
     uint16_t dct[26 * 32];
@@ -61,12 +61,12 @@ constexpr int kTableBytes = (sizeof(SharedTables) + 15) & ~15;
 // bit reader (FILL_BITS/peek_bits/get_bits, player.cpp:348-352, 495-514): MSB-first. `hi` holds
 // the current 32-bit word, `lo` the next one, `nx` the one after (prefetched), pos = bits of `hi`
 // already consumed. peek() is a single funnel shift. Reads run at most 12 bytes past the slice
-// (into the next start code); the ES blob carries 256 bytes of zero padding at its end.
+// plus the 8 prefetched ones (into the next start code); the ES blob carries 256 bytes of zero padding at its end.
 // ---------------------------------------------------------------------------------------------
 struct BitReader {
     const uint32_t* words;   // the whole ES blob as aligned 32-bit words (cudaMalloc alignment)
     uint32_t idx;            // next word to fetch
-    uint32_t hi, lo, nx_raw; // nx_raw: the prefetched word, still little-endian, so that its load is not waited for until the next refill
+    uint32_t hi, lo, nx_raw, nx2_raw;   // two prefetched words, still little-endian: their loads are not waited for until they are needed
     int pos;
 
     __device__ __forceinline__ uint32_t fetch_raw()
@@ -82,13 +82,13 @@ struct BitReader {
         words = (const uint32_t*)blob;
         idx = (uint32_t)(byte_off >> 2);
         pos = (int)(byte_off & 3) * 8;
-        hi = __byte_perm(fetch_raw(), 0, 0x0123); lo = __byte_perm(fetch_raw(), 0, 0x0123); nx_raw = fetch_raw();
+        hi = __byte_perm(fetch_raw(), 0, 0x0123); lo = __byte_perm(fetch_raw(), 0, 0x0123); nx_raw = fetch_raw(); nx2_raw = fetch_raw();
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }
     __device__ __forceinline__ void skip(int n)
     {
         pos += n;
-        if (pos >= 32) { pos -= 32; hi = lo; lo = __byte_perm(nx_raw, 0, 0x0123); nx_raw = fetch_raw(); }
+        if (pos >= 32) { pos -= 32; hi = lo; lo = __byte_perm(nx_raw, 0, 0x0123); nx_raw = nx2_raw; nx2_raw = fetch_raw(); }
     }
     __device__ __forceinline__ uint32_t get(int n)     // 1 <= n <= 32
     {
@@ -197,57 +197,86 @@ __device__ __forceinline__ uint32_t avg4x4(uint32_t a, uint32_t b, uint32_t c, u
     return ((e >> 2) & m) | (((o >> 2) & m) << 8);
 }
 
-// Reference pixels of one lane's 8-pixel segment: three consecutive aligned words of the row that
-// holds pixel (x, y) of a plane in the tiled frame, and of the row below when the vector has a
-// vertical half-pel. kLuma: 16-pixel tile rows, else 8-pixel chroma tile rows (plane 0/1).
-// Loads are issued early (before the IDCT) and consumed late, so their latency hides behind it.
+// ---- motion-compensation source: TMA-engine bulk copies of whole reference tiles into shared memory ----
+// A macroblock's prediction window (17 x 17 luma + 2 x 9 x 9 chroma at a half-pel vector) lies in at
+// most 2 x 2 tiles of the reference frame, and a tile (384 B: Y, block-4, block-5 chroma) is contiguous
+// in HBM, so one elected lane issues 1, 2 or 4 cp.async.bulk copies per macroblock, completion is
+// signalled on a per-warp mbarrier, and all lanes then read their pixels from shared memory. The copies
+// are issued before the IDCT work of the macroblock and waited for after it.
 struct PredWords { uint32_t a0, a1, a2, b0, b1, b2; };
 
-// 4-byte asynchronous global->shared copy (LDGSTS): no register, no scoreboard slot, completion via wait_group
-__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const void* gsrc)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
 }
 
-// st = this lane's column of the per-warp staging area: word k lives at st[k * 32]
+// Words of this lane's 8-pixel segment from the staged tiles. (x, y) = first pixel in plane
+// coordinates, (tx0, ty0) = tile of the window's top-left corner. kLuma: 16-pixel tile rows, else
+// 8-pixel chroma tile rows of plane 0/1.
 template <bool kLuma>
-__device__ __forceinline__ void pred_load(const uint8_t* ref, int plane, int x, int y, bool yh, bool inside, uint32_t* st)
+__device__ __forceinline__ void pred_words_staged(const uint8_t* st, int plane, int x, int y, int tx0, int ty0, bool yh, PredWords& w)
+{
+    constexpr int TS = kLuma ? 16 : 8, SH = kLuma ? 4 : 3;
+    const int plane_off = kLuma ? 0 : 256 + plane * 64;
+    const int xa = x & ~3;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        if (r == 1 && !yh) break;
+        const int yy = y + r;
+        const uint8_t* row = st + ((yy >> SH) - ty0) * (2 * EF_TILE) + plane_off + (yy & (TS - 1)) * TS;
+        uint32_t v[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int xw = xa + 4 * k;
+            const int tc = min(1, (xw >> SH) - tx0);               // the third word may fall outside the window: never used then
+            v[k] = *(const uint32_t*)(row + tc * EF_TILE + (xw & (TS - 1)));
+        }
+        if (r == 0) { w.a0 = v[0]; w.a1 = v[1]; w.a2 = v[2]; } else { w.b0 = v[0]; w.b1 = v[1]; w.b2 = v[2]; }
+    }
+}
+
+// Same words straight from HBM with coordinates clamped into the frame: only for vectors that
+// point outside the picture, where the reference reads whatever lies there (plain byte semantics of mocomp()).
+template <bool kLuma>
+__device__ __forceinline__ void pred_words_clamped(const uint8_t* ref, int plane, int x, int y, bool yh, PredWords& w)
 {
     constexpr int W = kLuma ? EF_W : EF_W / 2, H = kLuma ? EF_H : EF_H / 2, TS = kLuma ? 16 : 8, SH = kLuma ? 4 : 3;
-    const int rowstride = EF_MBW_MAX * EF_TILE;
     const int plane_off = kLuma ? 0 : 256 + plane * 64;
-    if (inside) {       // whole macroblock prediction lies in the frame (always, for streams the reference accepts)
-        const int xa = x & ~3, xi = xa & (TS - 1);
-        const int o0 = (y >> SH) * rowstride + plane_off + (y & (TS - 1)) * TS + (xa >> SH) * EF_TILE + xi;
-        const int o1 = o0 + (xi + 4 < TS ? 4 : EF_TILE + 4 - TS);
-        const int xj = (xi + 4) & (TS - 1);
-        const int o2 = o1 + (xj + 4 < TS ? 4 : EF_TILE + 4 - TS);
-        cp_async4(st, ref + o0); cp_async4(st + 32, ref + o1); cp_async4(st + 64, ref + o2);
-        if (yh) {
-            const int d = ((y & (TS - 1)) == TS - 1) ? rowstride - (TS - 1) * TS : TS;
-            cp_async4(st + 96, ref + o0 + d); cp_async4(st + 128, ref + o1 + d); cp_async4(st + 160, ref + o2 + d);
-        }
-    } else {            // plain byte semantics of mocomp() with coordinates clamped into the frame (the reference reads whatever lies there)
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            if (r == 1 && !yh) break;
-            const int yy = max(0, min(H - 1, y + r));
-            const int xa = max(0, min(W - 4, x & ~3)), xb = min(W - 4, xa + 4), xc = min(W - 4, xa + 8);
-            const int rowbase = (yy >> SH) * rowstride + plane_off + (yy & (TS - 1)) * TS;
-            cp_async4(st + r * 96, ref + rowbase + (xa >> SH) * EF_TILE + (xa & (TS - 1)));
-            cp_async4(st + r * 96 + 32, ref + rowbase + (xb >> SH) * EF_TILE + (xb & (TS - 1)));
-            cp_async4(st + r * 96 + 64, ref + rowbase + (xc >> SH) * EF_TILE + (xc & (TS - 1)));
-        }
+    for (int r = 0; r < 2; r++) {
+        if (r == 1 && !yh) break;
+        const int yy = max(0, min(H - 1, y + r));
+        const int xa = max(0, min(W - 4, x & ~3)), xb = min(W - 4, xa + 4), xc = min(W - 4, xa + 8);
+        const int rowbase = (yy >> SH) * EF_MBW_MAX * EF_TILE + plane_off + (yy & (TS - 1)) * TS;
+        const uint32_t v0 = *(const uint32_t*)(ref + rowbase + (xa >> SH) * EF_TILE + (xa & (TS - 1)));
+        const uint32_t v1 = *(const uint32_t*)(ref + rowbase + (xb >> SH) * EF_TILE + (xb & (TS - 1)));
+        const uint32_t v2 = *(const uint32_t*)(ref + rowbase + (xc >> SH) * EF_TILE + (xc & (TS - 1)));
+        if (r == 0) { w.a0 = v0; w.a1 = v1; w.a2 = v2; } else { w.b0 = v0; w.b1 = v1; w.b2 = v2; }
     }
 }
 
 // eight predicted pixels from the loaded words (the four cases of mocomp(), player.cpp:767-820)
-__device__ __forceinline__ void pred_finish(const uint32_t* st, int x, int xh, int yh, uint32_t& o0, uint32_t& o1)
+__device__ __forceinline__ void pred_finish(const PredWords& w, int x, int xh, int yh, uint32_t& o0, uint32_t& o1)
 {
-    PredWords w;
-    w.a0 = st[0]; w.a1 = st[32]; w.a2 = st[64];
-    if (yh) { w.b0 = st[96]; w.b1 = st[128]; w.b2 = st[160]; }
     const int sh = (x & 3) * 8;
     const uint32_t p0 = __funnelshift_r(w.a0, w.a1, sh), p1 = __funnelshift_r(w.a1, w.a2, sh);
     if (xh) {
@@ -385,7 +414,10 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     uint32_t* list = (uint32_t*)wbase + lane * kListEntries;
     uint8_t* hdr = wbase + kListBytes + lane * kHdrStride;
     int* dense = (int*)(wbase + kListBytes + kHdrBytes);
-    uint32_t* stage = (uint32_t*)(wbase + kListBytes + kHdrBytes + kDenseBytes) + lane;
+    uint8_t* stage = wbase + kListBytes + kHdrBytes + kDenseBytes;
+    uint64_t* bar = (uint64_t*)(stage + kStageBytes);
+    uint32_t bar_phase = 0;
+    if (lane == 0) mbar_init(bar, 1);
     uint32_t* ovf = D.k1_overflow + ((size_t)(blockIdx.x * kWarpsPerCta + warp) * 32 + lane) * (384 - kListEntries);
     for (int i = lane; i < kDenseBytes / 4; i += 32) ((uint32_t*)dense)[i] = 0;
     __syncthreads();
@@ -537,11 +569,16 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             const int cx = hx >> 1, cy = hy >> 1;                                   // Q3: floor
             const int lx = (hx >> 1) + phalf * 8, ly = (hy >> 1) + prow;
             const int kx = cx >> 1, ky = (cy >> 1) + crow;
-            if (!intra_r) {
-                const bool inside = hx >= 0 && hy >= 0 && (hx >> 1) + 16 + (hx & 1) <= EF_W && (hy >> 1) + 16 + (hy & 1) <= EF_H;
-                pred_load<true>(ref, 0, lx, ly, hy & 1, inside, stage);
-                if (lane < 16) pred_load<false>(ref, cplane, kx, ky, cy & 1, inside, stage + 192);
-                asm volatile("cp.async.commit_group;");
+            const int X0 = hx >> 1, Y0 = hy >> 1, tx0 = X0 >> 4, ty0 = Y0 >> 4;
+            // whole prediction window inside the picture (always, for streams the reference accepts)
+            const bool inside = hx >= 0 && hy >= 0 && X0 + 16 + (hx & 1) <= EF_W && Y0 + 16 + (hy & 1) <= EF_H;
+            if (!intra_r && inside && lane == 0) {
+                const int ntx = ((X0 + 15 + (hx & 1)) >> 4) - tx0 + 1, nty = ((Y0 + 15 + (hy & 1)) >> 4) - ty0 + 1;   // 1 or 2 each
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of the staging area are done
+                mbar_expect_tx(bar, (uint32_t)(ntx * nty * EF_TILE));
+                for (int ty = 0; ty < nty; ty++)
+                    for (int tx = 0; tx < ntx; tx++)
+                        bulk_g2s(stage + (ty * 2 + tx) * EF_TILE, ref + ef_tile_offset(tx0 + tx, ty0 + ty), EF_TILE, bar);
             }
 
             // expand the coefficient list into the dense scratch
@@ -622,9 +659,18 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             // ---- finish the prediction, combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
             uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
             if (!intra_r) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                pred_finish(stage, lx, hx & 1, hy & 1, py0, py1);
-                if (lane < 16) pred_finish(stage + 192, kx, cx & 1, cy & 1, pc0, pc1);
+                PredWords wy, wc;
+                if (inside) {
+                    mbar_wait(bar, bar_phase);
+                    bar_phase ^= 1;
+                    pred_words_staged<true>(stage, 0, lx, ly, tx0, ty0, hy & 1, wy);
+                    if (lane < 16) pred_words_staged<false>(stage, cplane, kx, ky, tx0, ty0, cy & 1, wc);
+                } else {
+                    pred_words_clamped<true>(ref, 0, lx, ly, hy & 1, wy);
+                    if (lane < 16) pred_words_clamped<false>(ref, cplane, kx, ky, cy & 1, wc);
+                }
+                pred_finish(wy, lx, hx & 1, hy & 1, py0, py1);
+                if (lane < 16) pred_finish(wc, kx, cx & 1, cy & 1, pc0, pc1);
             }
             {
                 const bool coded = (cbp >> rblk) & 1, aborted = (abm >> rblk) & 1, n1 = (n1m >> rblk) & 1;
