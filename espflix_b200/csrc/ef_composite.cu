@@ -114,10 +114,17 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
         w[3] = (((p1 << 8) & 0xFF000000u) | (p0 >> 16)) + (cb << 8);
     } else {
         // blank and vsync lines, and the part of an active line outside the blit span (which still
-        // shows what blanking() last left in the ping-pong buffer: sync, burst, BLACK)
+        // shows what blanking() last left in the ping-pong buffer: sync, burst, BLACK). Most chunks
+        // lie wholly inside one constant region: decide per chunk, fall back to per-sample only at
+        // the burst and on the vsync lines.
+        const uint32_t SYNC2 = 0x00000000u, BLACK2 = 0x18001800u;
+        if (line < G::VSYNC && x0 + 8 <= G::HSYNC) w[0] = w[1] = w[2] = w[3] = SYNC2;
+        else if (line < G::VSYNC && (x0 >= G::BURST_START + G::BURST_W || (x0 >= G::HSYNC && x0 + 8 <= G::BURST_START))) w[0] = w[1] = w[2] = w[3] = BLACK2;
+        else {
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            w[i] = blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i) | (blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i + 1) << 16);
+            for (int i = 0; i < 4; i++)
+                w[i] = blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i) | (blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i + 1) << 16);
+        }
     }
     __stcs((uint4*)out, make_uint4(w[0], w[1], w[2], w[3]));               // streaming store: the field is not re-read by this kernel
 }

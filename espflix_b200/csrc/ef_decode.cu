@@ -211,21 +211,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t sbar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+// one reference tile (384 B) HBM -> shared memory through the TMA engine; sdst / sbar are shared-window addresses
+__device__ __forceinline__ void bulk_tile(uint32_t sdst, const uint8_t* gsrc, uint32_t sbar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 384, [%2];"
+                 ::"r"(sdst), "l"(gsrc), "r"(sbar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t sbar, uint32_t parity)
 {
     uint32_t ok;
     do {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+                     : "=r"(ok) : "r"(sbar), "r"(parity) : "memory");
     } while (!ok);
 }
 
@@ -236,21 +237,18 @@ template <bool kLuma>
 __device__ __forceinline__ void pred_words_staged(const uint8_t* st, int plane, int x, int y, int tx0, int ty0, bool yh, PredWords& w)
 {
     constexpr int TS = kLuma ? 16 : 8, SH = kLuma ? 4 : 3;
-    const int plane_off = kLuma ? 0 : 256 + plane * 64;
-    const int xa = x & ~3;
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        if (r == 1 && !yh) break;
-        const int yy = y + r;
-        const uint8_t* row = st + ((yy >> SH) - ty0) * (2 * EF_TILE) + plane_off + (yy & (TS - 1)) * TS;
-        uint32_t v[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int xw = xa + 4 * k;
-            const int tc = min(1, (xw >> SH) - tx0);               // the third word may fall outside the window: never used then
-            v[k] = *(const uint32_t*)(row + tc * EF_TILE + (xw & (TS - 1)));
-        }
-        if (r == 0) { w.a0 = v[0]; w.a1 = v[1]; w.a2 = v[2]; } else { w.b0 = v[0]; w.b1 = v[1]; w.b2 = v[2]; }
+    const int xa = x & ~3, xi = xa & (TS - 1), yi = y & (TS - 1);
+    // word 0, then +4 bytes each, hopping to the next staged tile column (+384) at the end of a tile row;
+    // a hop out of the 2 x 2 window can only happen for the third word when it is not used: keep it inside
+    const int o0 = ((y >> SH) - ty0) * (2 * EF_TILE) + ((xa >> SH) - tx0) * EF_TILE + (kLuma ? 0 : 256 + plane * 64) + yi * TS + xi;
+    const int o1 = o0 + (xi + 4 < TS ? 4 : EF_TILE + 4 - TS);
+    const int xj = (xi + 4) & (TS - 1);
+    int o2 = o1 + (xj + 4 < TS ? 4 : EF_TILE + 4 - TS);
+    if (((xa + 8) >> SH) - tx0 > 1) o2 = o1;
+    w.a0 = *(const uint32_t*)(st + o0); w.a1 = *(const uint32_t*)(st + o1); w.a2 = *(const uint32_t*)(st + o2);
+    if (yh) {
+        const int d = yi == TS - 1 ? 2 * EF_TILE - (TS - 1) * TS : TS;    // next row: same tile, or the tile below
+        w.b0 = *(const uint32_t*)(st + o0 + d); w.b1 = *(const uint32_t*)(st + o1 + d); w.b2 = *(const uint32_t*)(st + o2 + d);
     }
 }
 
@@ -416,6 +414,7 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     int* dense = (int*)(wbase + kListBytes + kHdrBytes);
     uint8_t* stage = wbase + kListBytes + kHdrBytes + kDenseBytes;
     uint64_t* bar = (uint64_t*)(stage + kStageBytes);
+    const uint32_t sstage = smem_u32(stage), sbar = smem_u32(bar);
     uint32_t bar_phase = 0;
     if (lane == 0) mbar_init(bar, 1);
     uint32_t* ovf = D.k1_overflow + ((size_t)(blockIdx.x * kWarpsPerCta + warp) * 32 + lane) * (384 - kListEntries);
@@ -573,12 +572,16 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             // whole prediction window inside the picture (always, for streams the reference accepts)
             const bool inside = hx >= 0 && hy >= 0 && X0 + 16 + (hx & 1) <= EF_W && Y0 + 16 + (hy & 1) <= EF_H;
             if (!intra_r && inside && lane == 0) {
-                const int ntx = ((X0 + 15 + (hx & 1)) >> 4) - tx0 + 1, nty = ((Y0 + 15 + (hy & 1)) >> 4) - ty0 + 1;   // 1 or 2 each
+                const bool two_x = ((X0 + 15 + (hx & 1)) >> 4) != tx0, two_y = ((Y0 + 15 + (hy & 1)) >> 4) != ty0;
+                const uint8_t* src = ref + ef_tile_offset(tx0, ty0);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of the staging area are done
-                mbar_expect_tx(bar, (uint32_t)(ntx * nty * EF_TILE));
-                for (int ty = 0; ty < nty; ty++)
-                    for (int tx = 0; tx < ntx; tx++)
-                        bulk_g2s(stage + (ty * 2 + tx) * EF_TILE, ref + ef_tile_offset(tx0 + tx, ty0 + ty), EF_TILE, bar);
+                mbar_expect_tx(sbar, (uint32_t)EF_TILE << ((int)two_x + (int)two_y));
+                bulk_tile(sstage, src, sbar);
+                if (two_x) bulk_tile(sstage + EF_TILE, src + EF_TILE, sbar);
+                if (two_y) {
+                    bulk_tile(sstage + 2 * EF_TILE, src + EF_MBW_MAX * EF_TILE, sbar);
+                    if (two_x) bulk_tile(sstage + 3 * EF_TILE, src + (EF_MBW_MAX + 1) * EF_TILE, sbar);
+                }
             }
 
             // expand the coefficient list into the dense scratch
@@ -661,7 +664,7 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             if (!intra_r) {
                 PredWords wy, wc;
                 if (inside) {
-                    mbar_wait(bar, bar_phase);
+                    mbar_wait(sbar, bar_phase);
                     bar_phase ^= 1;
                     pred_words_staged<true>(stage, 0, lx, ly, tx0, ty0, hy & 1, wy);
                     if (lane < 16) pred_words_staged<false>(stage, cplane, kx, ky, tx0, ty0, cy & 1, wc);
