@@ -56,10 +56,11 @@ def workload_config(n_gpus, streams):
     }
 
 
-def make_streams(streams):
-    from espflix_b200 import synth
+def make_streams(streams, rank=0):
+    """D distinct synthetic streams (rank-specific window of the seed space) replicated to `streams`."""
+    from espflix_b200 import shard, synth
     d = min(DISTINCT, streams)
-    gen = synth.generate_many(d, n_pictures=PICTURES, gop=PICTURES, slices=12)
+    gen = synth.generate_many(d, first_index=shard.stream_seed_index(rank, 0, d), n_pictures=PICTURES, gop=PICTURES, slices=12)
     return gen, [gen[i % d][0] for i in range(streams)]
 
 
@@ -196,10 +197,12 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     streams = args.streams
-    gen, stream_list = make_streams(streams)
+    gen, stream_list = make_streams(streams, rank)
     sizes = np.diff(gen[0][1].astype(np.int64))
     ctx = espflix_b200.Context(n_streams=streams, max_pictures=PICTURES, max_slices_per_picture=12,
                                es_capacity=sum(len(s) for s in stream_list) + 4096, device=local, fields=True)

@@ -215,11 +215,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t sbar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"(bytes) : "memory");
 }
-// one reference tile (384 B) HBM -> shared memory through the TMA engine; sdst / sbar are shared-window addresses
-__device__ __forceinline__ void bulk_tile(uint32_t sdst, const uint8_t* gsrc, uint32_t sbar)
+// one or two horizontally adjacent reference tiles (384 / 768 contiguous bytes) HBM -> shared memory
+// through the TMA engine; sdst / sbar are shared-window addresses
+__device__ __forceinline__ void bulk_tiles(uint32_t sdst, const uint8_t* gsrc, uint32_t bytes, uint32_t sbar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 384, [%2];"
-                 ::"r"(sdst), "l"(gsrc), "r"(sbar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(sbar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t sbar, uint32_t parity)
 {
@@ -498,7 +499,9 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                 }
                 const uint32_t bits = br.peek();
                 const int lz = min(__clz(bits), 12);               // row 12 / 25 = not a code
-                const uint32_t e = T.dct[(n == 0 ? 13 * 32 : 0) + lz * 32 + ((bits << (lz + 1)) >> 27)];
+                // index = row * 32 + the five bits after the leading one; (bits << lz) >> 26 is "1xxxxx" = 32 + those bits
+                const int ctx = n == 0 ? 13 * 32 - 32 : -32;       // first-coefficient context lives in rows 13..25
+                const uint32_t e = T.dct[ctx + lz * 32 + (int)((bits << lz) >> 26)];
                 int len = e & 31, run = (e >> 5) & 31, level = (int)(e >> 10);
                 bool end_block = false, derail = false;
                 if (level) {
@@ -574,14 +577,12 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             if (!intra_r && inside && lane == 0) {
                 const bool two_x = ((X0 + 15 + (hx & 1)) >> 4) != tx0, two_y = ((Y0 + 15 + (hy & 1)) >> 4) != ty0;
                 const uint8_t* src = ref + ef_tile_offset(tx0, ty0);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of the staging area are done
-                mbar_expect_tx(sbar, (uint32_t)EF_TILE << ((int)two_x + (int)two_y));
-                bulk_tile(sstage, src, sbar);
-                if (two_x) bulk_tile(sstage + EF_TILE, src + EF_TILE, sbar);
-                if (two_y) {
-                    bulk_tile(sstage + 2 * EF_TILE, src + EF_MBW_MAX * EF_TILE, sbar);
-                    if (two_x) bulk_tile(sstage + 3 * EF_TILE, src + (EF_MBW_MAX + 1) * EF_TILE, sbar);
-                }
+                // (the staging area is only ever written by these copies and read with plain loads that have
+                // all completed before the __syncwarp() that ended the previous macroblock)
+                const uint32_t row_bytes = two_x ? 2 * EF_TILE : EF_TILE;           // tiles of one row are contiguous in HBM
+                mbar_expect_tx(sbar, row_bytes << (int)two_y);
+                bulk_tiles(sstage, src, row_bytes, sbar);
+                if (two_y) bulk_tiles(sstage + 2 * EF_TILE, src + EF_MBW_MAX * EF_TILE, row_bytes, sbar);
             }
 
             // expand the coefficient list into the dense scratch
