@@ -43,7 +43,7 @@ def build_cuda(force=False, verbose_ptxas=False):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "espflix_b200.h"))
     if force or _newer(LIB, deps):
-        flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose_ptxas else [])
+        flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose_ptxas else []) + os.environ.get("EF_NVCC_DEFS", "").split()   # tuning experiments
         r = _run([nvcc_path()] + flags + ["-o", LIB] + srcs, cwd=CSRC)
         return r.stderr
     return ""

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "ef_video_init": (_I, [_VP, _I]),
     "ef_video_geometry": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "ef_composite_field": (_I, [_VP, _I, _I, _VP]),
+    "ef_video_set_scroll": (_I, [_VP, _I]),
+    "ef_video_set_overlay": (_I, [_VP, _VP, _I, _I]),
     "ef_read_field": (_I, [_VP, _I, _VP]),
     "ef_video_isr": (_I, [_VP, _I, _I, _VP]),
     "ef_blit": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I]),
@@ -207,6 +209,15 @@ class Context:
 
     def composite_field(self, fb=-1, frame_counter=0, stream=0):
         self._check(self.lib.ef_composite_field(self._h, fb, frame_counter, stream))
+
+    def set_scroll(self, hscroll):
+        self._check(self.lib.ef_video_set_scroll(self._h, hscroll))
+
+    def set_overlay(self, bitmap, blend, progress):
+        if bitmap is not None:
+            bitmap = np.ascontiguousarray(bitmap, dtype=np.uint8)
+            assert bitmap.size == 1280
+        self._check(self.lib.ef_video_set_overlay(self._h, _ptr(bitmap), blend, progress))
 
     def read_field(self, s):
         w, n = self.geometry()

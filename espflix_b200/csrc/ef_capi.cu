@@ -25,7 +25,7 @@ __global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint6
 size_t ef_decode_smem_bytes();
 cudaError_t ef_decode_configure();
 cudaError_t ef_launch_decode(const EfDev* dev, int pic, int ctas, cudaStream_t stream);
-cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, cudaStream_t stream);
+cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream);
 cudaError_t ef_launch_blit(const EfDev* dev, int stream_index, int fb, int line, int x, int width, int frame_counter, uint16_t* dst, cudaStream_t stream);
 
 namespace {
@@ -105,6 +105,8 @@ struct ef_ctx {
     uint8_t* d_default_intra = nullptr;
     uint32_t* d_color_tab = nullptr;
     int16_t* d_pal_burst = nullptr;
+    uint8_t* d_overlay = nullptr;     // _video_composite bitmap, 16 x 80
+    EfPresent present = { 0, 0, 0, nullptr };
     bool indexed = false, submitted = false, video = false;
     uint64_t launches = 0;
     uint64_t es_bytes = 0;
@@ -198,7 +200,8 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     A(h.info, 8);
     EfTables* dt; A(dt, 1);
     A(h.k1_overflow, (size_t)c->sm_count * EF_K1_WARPS * 32 * (384 - EF_K1_LIST));
-    A(c->d_color_tab, 768); A(c->d_pal_burst, 128); A(c->d_default_intra, 64);
+    A(c->d_color_tab, 768); A(c->d_pal_burst, 128); A(c->d_default_intra, 64); A(c->d_overlay, 1280);
+    c->present.bitmap = c->d_overlay;
     if (cfg->fields) { h.field_stride = EF_PAL_FIELD_SAMPLES; A(h.fields, (size_t)n * h.field_stride); }
     A(c->d, 1);
 #undef A
@@ -212,6 +215,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     CK(cudaMemcpy(c->d_default_intra, ef_default_intra_ptr(), 64, cudaMemcpyHostToDevice));
     CK(cudaMemset(c->d_es, 0, cfg->es_capacity + 1024));
     CK(cudaMemset(c->d_es_off, 0, ((size_t)n + 1) * 8));
+    CK(cudaMemset(c->d_overlay, 0, 1280));
     CK(cudaMemcpy(c->d, &h, sizeof(h), cudaMemcpyHostToDevice));
     *out = c;
     rc = ef_reset(c);
@@ -487,8 +491,25 @@ int ef_composite_field(ef_ctx* c, int fb, int frame_counter, void* stream)
     if (!c) return fail(EF_EINVAL, "null context");
     if (!c->h.fields) return fail(EF_ESTATE, "context was created without field buffers (ef_config.fields = 0)");
     if (fb < -2 || fb > 1) return fail(EF_EINVAL, "fb must be 0, 1, -1 or -2");
-    CK(ef_launch_composite(c->d, c->cfg.n_streams, c->h.geo, fb, frame_counter, (cudaStream_t)stream));
+    CK(ef_launch_composite(c->d, c->cfg.n_streams, c->h.geo, fb, frame_counter, c->present, (cudaStream_t)stream));
     c->launches++;
+    return EF_OK;
+}
+
+int ef_video_set_scroll(ef_ctx* c, int hscroll)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (hscroll <= -EF_W || hscroll >= EF_W || (hscroll & 7)) return fail(EF_EINVAL, "hscroll must be a multiple of 8 in (-352, 352)");
+    c->present.hscroll = hscroll;
+    return EF_OK;
+}
+
+int ef_video_set_overlay(ef_ctx* c, const uint8_t* bitmap, int blend, int progress)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (blend != 0 && !bitmap && c->present.blend == 0) return fail(EF_EINVAL, "overlay bitmap required when blend != 0");
+    if (bitmap) { CK(cudaDeviceSynchronize()); CK(cudaMemcpy(c->d_overlay, bitmap, 1280, cudaMemcpyHostToDevice)); }
+    c->present.blend = blend; c->present.progress = progress;
     return EF_OK;
 }
 

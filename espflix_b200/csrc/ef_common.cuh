@@ -29,8 +29,12 @@
 #define EF_MBW_MAX 22
 #define EF_MBH_MAX 12
 #define EF_TILE 384          // bytes per macroblock tile: 256 Y + 64 + 64 chroma
+#ifndef EF_K1_WARPS
 #define EF_K1_WARPS 15       // warps per K1 CTA (one CTA per SM; shared-memory bound)
+#endif
+#ifndef EF_K1_LIST
 #define EF_K1_LIST 80        // per-lane coefficient list entries kept in shared memory (rest spills to HBM)
+#endif
 
 // ---- decode tables (built on the host by ef_tables.cpp from ISO 11172-2 Annex B) -------------
 // All VLC tables are indexed by (leading zeros, next 5 bits) so that one CLZ + one shared-memory
@@ -85,6 +89,13 @@ struct __align__(16) EfWork {   // one slice of one stream for one picture index
 struct EfGeometry {          // video.cpp:572-630, values probe-verified in tests/golden/composite_pins.json
     int ntsc, line_width, line_count, hsync, hsync_long, hsync_short, burst_start, burst_width, active_start;
     int active_top, vsync_start, blit_start;      // blit_start = active_start + 16 (+80 PAL)
+};
+
+struct EfPresent {           // presentation state of video_isr beyond the plain frame (video.cpp:839-887, 1146-1154)
+    int hscroll;             // _hscroll: multiple of 8 in -344..344; negative scrolls in from the other side
+    int blend;               // _video_composite_blend: 0 off, -1 or >= 32 full, 1..31 fading
+    int progress;            // _video_composite_progress
+    const uint8_t* bitmap;   // _video_composite[16][80]
 };
 
 struct EfDev {               // device-visible context (lives in device memory)

@@ -60,29 +60,43 @@ __constant__ uint32_t c_dither[8] = {                                     // dit
 
 }  // namespace
 
-// grid: x = 16-byte chunks of one field / 256, y = stream
+// grid: x = threads of one field / 256, y = stream. A warp covers 16 consecutive 16-byte chunks of TWO
+// consecutive lines (lanes 0-15 the even line, lanes 16-31 the odd one): in the tiled frame the two luma
+// rows of a tile share 32-byte sectors and both lines read the same chroma row, so every sector the warp
+// fetches is used whole. Stores stay 256 contiguous bytes per half-warp.
 template <bool kNtsc>
 __global__ void __launch_bounds__(256)
-ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
+ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter, const EfPresent pr)
 {
     using G = Geo<kNtsc>;
     constexpr int CPL = G::W / 8;                                          // 16-byte chunks per line
+    constexpr int GROUPS = (CPL + 15) / 16;                                // warps per line pair
     const EfDev& D = *Dp;
     const uint32_t* tab = D.color_tab;                                     // 3 KB LUT: lives in L1 through the read-only path
-    const uint32_t c = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     const uint32_t stream = blockIdx.y;
-    if (c >= (uint32_t)(CPL * G::LINES)) return;
-    const int line = (int)(c / CPL), k = (int)(c - (uint32_t)line * CPL);
+    const int pair = (int)(t / (GROUPS * 32)), r = (int)(t - (uint32_t)pair * (GROUPS * 32));
+    const int lane = r & 31;
+    const int line = 2 * pair + (lane >> 4), k = (r >> 5) * 16 + (lane & 15);
+    if (pair >= G::LINES / 2 || k >= CPL) return;
     const int x0 = k * 8;
-    uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)c * 8;
+    uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)(line * CPL + k) * 8;
 
     const int fl = line - G::TOP;                                          // frame line 0..191 on active lines
     const bool active = fl >= 0 && fl < EF_H && fb_sel != -2;              // -2: no frame presented yet (video.cpp:1140)
     uint32_t w[4];
     if (active && x0 >= G::BLIT && x0 < G::BLIT + 2 * EF_W) {
-        const int fb = fb_sel >= 0 ? fb_sel : (int)((D.base_pics[stream] + D.n_pics[stream]) & 1u);
+        int fb = fb_sel >= 0 ? fb_sel : (int)((D.base_pics[stream] + D.n_pics[stream]) & 1u);
+        // two-frame horizontal scroll (video.cpp:1146-1154): blit(f, dst, i, h, 352-h) then blit(f^1, dst + (352-h)*2, i, 0, h)
+        int h = pr.hscroll;
+        if (h < 0) { h += EF_W; fb ^= 1; }
+        const int qd = (x0 - G::BLIT) >> 3;                                // 4-pixel group of the destination, 0..87
+        const int split = (EF_W - h) >> 2;                                 // first group drawn by the second blit
+        const bool second = qd >= split;
+        if (second) fb ^= 1;
+        const int q = second ? qd - split : qd + (h >> 2);                 // 4-pixel group of the source frame
+        const bool call_start = second ? q == 0 : qd == 0;                 // blit() starts its luma carry at 0
         const uint8_t* f = D.frames + ef_frame_offset((int)stream, fb);
-        const int q = (x0 - G::BLIT) >> 3;                                 // 4-pixel group index 0..87
         const uint32_t dither = c_dither[(fl & 3) + ((frame_counter & 1) << 2)];
         // tiled frame (ef_common.cuh): 4 luma pixels of group q sit in tile q>>2, the 2 chroma samples too
         const int cy = fl >> 1;
@@ -103,7 +117,7 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
         }
         const uint32_t ca = chroma_word(tab, u2, v2, vt), cb = chroma_word(tab, u2 >> 8, v2 >> 8, vt);
         uint32_t lum = 0;                                                  // carry = pixel 3 of the previous group, 0 at the line start
-        if (q > 0) lum = ((((*(const uint32_t*)(yrow + ((q - 1) >> 2) * EF_TILE + ((q - 1) & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
+        if (!call_start) lum = ((((*(const uint32_t*)(yrow + ((q - 1) >> 2) * EF_TILE + ((q - 1) & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
         uint32_t p0 = (*(const uint32_t*)(yrow + ycol) + dither) & 0xFCFCFCFCu;   // video.cpp:716-733, verbatim packed arithmetic
         uint32_t p1 = ((p0 >> 1) + (p0 >> 9)) & 0xFCFCFCFCu;
         p0 >>= 2; p1 >>= 2;
@@ -118,7 +132,20 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter)
         // lie wholly inside one constant region: decide per chunk, fall back to per-sample only at
         // the burst and on the vsync lines.
         const uint32_t SYNC2 = 0x00000000u, BLACK2 = 0x18001800u;
-        if (line < G::VSYNC && x0 + 8 <= G::HSYNC) w[0] = w[1] = w[2] = w[3] = SYNC2;
+        const int ol = line - (G::TOP + EF_H + 2);                         // overlay line 0..15 (video.cpp:1183-1189)
+        if (pr.blend != 0 && ol >= 0 && ol < 16 && x0 >= G::BLIT + 16 && x0 < G::BLIT + 16 + 160 + 16 + 480) {
+            // composite(), video.cpp:845-887: 80 bitmap bytes -> 160 samples, then (lines 3..8) a 480-sample progress bar
+            int scale = 255 / 4;
+            if (pr.blend != -1 && pr.blend < 32) scale = (scale * pr.blend) >> 5;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int s = x0 + 2 * i - (G::BLIT + 16);                 // both samples of a word share the source byte / bar step
+                uint32_t v = 0x1800u;
+                if (s < 160) v = 0x1800u + (uint32_t)pr.bitmap[ol * 80 + (s >> 1)] * (uint32_t)scale;
+                else if (s >= 176 && ol >= 3 && ol <= 8) v = 0x1800u + ((uint32_t)scale << ((((s - 176) >> 2) * 2 < pr.progress) ? 8 : 7));
+                w[i] = (v & 0xFFFFu) | (v << 16);
+            }
+        } else if (line < G::VSYNC && x0 + 8 <= G::HSYNC) w[0] = w[1] = w[2] = w[3] = SYNC2;
         else if (line < G::VSYNC && (x0 >= G::BURST_START + G::BURST_W || (x0 >= G::HSYNC && x0 + 8 <= G::BURST_START))) w[0] = w[1] = w[2] = w[3] = BLACK2;
         else {
 #pragma unroll
@@ -170,12 +197,13 @@ __global__ void ef_blit_kernel(const EfDev* __restrict__ Dp, int stream, int fb,
     o[3] = (((p1 << 8) & 0xFF000000u) | (p0 >> 16)) + (cb << 8);
 }
 
-cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, cudaStream_t stream)
+cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream)
 {
-    const unsigned chunks = (unsigned)(g.line_width >> 3) * (unsigned)g.line_count;
-    const dim3 grid((chunks + 255) / 256, (unsigned)n_streams);
-    if (g.ntsc) ef_composite_kernel<true><<<grid, 256, 0, stream>>>(dev, fb, frame_counter);
-    else ef_composite_kernel<false><<<grid, 256, 0, stream>>>(dev, fb, frame_counter);
+    const unsigned groups = ((unsigned)(g.line_width >> 3) + 15) / 16;
+    const unsigned threads = groups * 32 * (unsigned)(g.line_count / 2);   // both standards have an even line count
+    const dim3 grid((threads + 255) / 256, (unsigned)n_streams);
+    if (g.ntsc) ef_composite_kernel<true><<<grid, 256, 0, stream>>>(dev, fb, frame_counter, pr);
+    else ef_composite_kernel<false><<<grid, 256, 0, stream>>>(dev, fb, frame_counter, pr);
     return cudaGetLastError();
 }
 

@@ -51,6 +51,15 @@ extern "C" void video_isr(volatile void* buf);                       // fills on
 void blit(Frame* frame, uint16_t* dst, int line, int x, int width);   // video.cpp:690
 extern volatile int _line_counter;
 extern volatile int _frame_counter;
+extern int16_t _hscroll;                                             // two-frame scroll, multiple of 8 (video.cpp:940)
+
+// time/progress overlay of the display side (video.h:52-57)
+#define VIDEO_COMPOSITE_WIDTH 80
+#define VIDEO_COMPOSITE_HEIGHT 16
+#define VIDEO_COMPOSITE_PROGRESS_WIDTH (352 - VIDEO_COMPOSITE_WIDTH - 32)
+extern uint8_t _video_composite[VIDEO_COMPOSITE_HEIGHT * VIDEO_COMPOSITE_WIDTH];
+extern int _video_composite_blend;
+extern int _video_composite_progress;
 
 // test/tooling hook: observe every push_video() (the reference's harnesses stub push_video instead)
 typedef void (*ef_push_video_hook)(Frame* f, int front, int64_t pts, int mode, void* user);

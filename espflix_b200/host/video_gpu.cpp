@@ -13,6 +13,10 @@
 
 volatile int _line_counter = 0;
 volatile int _frame_counter = 0;
+int16_t _hscroll = 0;
+uint8_t _video_composite[VIDEO_COMPOSITE_HEIGHT * VIDEO_COMPOSITE_WIDTH];
+int _video_composite_blend = 0;
+int _video_composite_progress = 0;
 
 namespace {
 ef_ctx* g_ctx = nullptr;
@@ -34,10 +38,10 @@ bool ensure_ctx()
     return true;
 }
 
-void upload(Frame* f)
+void upload(Frame* f, int fb = 0)
 {
     for (int s = 0; s < FB_SLICES; s++) memcpy(g_staging.data() + (size_t)s * EF_STRIP_BYTES, f->_slices[s], EF_STRIP_BYTES);
-    if (ef_write_frame(g_ctx, 0, 0, g_staging.data()) != EF_OK) fprintf(stderr, "video: %s\n", ef_last_error());
+    if (ef_write_frame(g_ctx, 0, fb, g_staging.data()) != EF_OK) fprintf(stderr, "video: %s\n", ef_last_error());
 }
 }  // namespace
 
@@ -71,13 +75,22 @@ extern "C" void video_isr(volatile void* vbuf)    // video.cpp:1122
     const int i = _line_counter;
     if (i == 0) {                                  // new field: one K2 launch
         int fb = -2;                               // no frame presented yet: active lines are blank lines
-        if (g_frames && g_current != -1) { upload(&g_frames[g_current]); fb = 0; }
+        if (g_frames && g_current != -1) {
+            upload(&g_frames[g_current], 0);
+            if (_hscroll) upload(&g_frames[g_current ^ 1], 1);   // the frame scrolling in (video.cpp:1146-1154)
+            fb = 0;
+        }
+        ef_video_set_scroll(g_ctx, _hscroll & ~7);
+        ef_video_set_overlay(g_ctx, _video_composite, _video_composite_blend, _video_composite_progress);
         if (ef_composite_field(g_ctx, fb, _frame_counter, nullptr) != EF_OK || ef_read_field(g_ctx, 0, g_field.data()) != EF_OK)
             fprintf(stderr, "video: %s\n", ef_last_error());
     }
     memcpy((void*)vbuf, g_field.data() + (size_t)i * g_line_width, (size_t)g_line_width * 2);
     _line_counter = i + 1;
-    if (_line_counter == g_line_count) { _line_counter = 0; _frame_counter = _frame_counter + 1; }
+    if (_line_counter == g_line_count) {           // end of field (video.cpp:1192-1197)
+        _line_counter = 0; _frame_counter = _frame_counter + 1;
+        if (_video_composite_blend > 0) --_video_composite_blend;
+    }
 }
 
 void blit(Frame* frame, uint16_t* dst, int line, int x, int width)   // video.cpp:690

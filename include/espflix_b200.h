@@ -115,6 +115,14 @@ int ef_video_geometry(ef_ctx* ctx, int* line_width, int* line_count);
  * active lines come out as blank lines, the reference's _current_frame == -1 case, video.cpp:1140),
  * `frame_counter` = the reference's _frame_counter (dither phase), one launch. */
 int ef_composite_field(ef_ctx* ctx, int fb, int frame_counter, void* stream);
+/* Presentation extras of video_isr, applied by the next ef_composite_field calls:
+ * ef_video_set_scroll   the reference's _hscroll two-frame scroll (video.cpp:1146-1154): the other frame
+ *                       store of each stream scrolls in; hscroll = multiple of 8 in (-352, 352), 0 = off.
+ * ef_video_set_overlay  _video_composite / _video_composite_blend / _video_composite_progress
+ *                       (video.cpp:839-887): 80x16 bitmap (may be NULL to keep the last one), blend 0 = off,
+ *                       -1 or >= 32 = full, 1..31 = fading; progress 0..240. */
+int ef_video_set_scroll(ef_ctx* ctx, int hscroll);
+int ef_video_set_overlay(ef_ctx* ctx, const uint8_t* bitmap80x16, int blend, int progress);
 int ef_read_field(ef_ctx* ctx, int stream_index, uint16_t* dst /* line_count*line_width */);
 /* video_isr-style single line fetch from the last synthesised field of stream_index. */
 int ef_video_isr(ef_ctx* ctx, int stream_index, int line, uint16_t* buf /* line_width */);

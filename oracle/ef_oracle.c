@@ -713,7 +713,32 @@ static void pal_sync_half(const efo_video* v, uint16_t* line, int width, int lng
     fill16(line + sw, (uint16_t)BLANKING_LEVEL, width - sw);
 }
 
-void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uint16_t* out)   /* video_isr, video.cpp:1122 */
+/* composite(), video.cpp:845-887: overlay bitmap scaled into the black level, progress bar on lines 3..8 */
+static void overlay(const efo_video* v, uint16_t* dst, int line, const uint8_t* bitmap, int blend, int progress)
+{
+    if (!blend) return;
+    if (!v->ntsc) dst += 80;
+    dst += 16;
+    const uint8_t* src = bitmap + line * 80;
+    int scale = 255 / 4;
+    if (blend != -1 && blend < 32) scale = (scale * blend) >> 5;
+    for (int n = 0; n < 80; n++) {
+        uint32_t p = BLACK_LEVEL + src[n] * scale;
+        st32(dst, (p << 16) | p);
+        dst += 2;
+    }
+    if (line < 3 || line > 8) return;
+    dst += 16;
+    uint32_t c0 = BLACK_LEVEL + (scale << 8), c1 = BLACK_LEVEL + (scale << 7);
+    for (int i = 0; i < 352 - 80 - 32; i += 2) {
+        uint32_t c = i < progress ? c0 : c1;
+        st32(dst, (c << 16) | c); st32(dst + 2, (c << 16) | c);
+        dst += 4;
+    }
+}
+
+void efo_field_ex(const efo_video* v, const uint8_t* strips_a, const uint8_t* strips_b, int frame_counter, int hscroll,
+                  const uint8_t* bitmap, int blend, int progress, uint16_t* out)   /* video_isr, video.cpp:1122 */
 {
     static const uint8_t sync_type[8] = { 0, 0, 0, 3, 3, 2, 0, 0 };
     uint16_t* lb[2];
@@ -727,15 +752,29 @@ void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uin
         if (i >= top && i < bottom) {
             fill16(buf, (uint16_t)SYNC_LEVEL, v->hsync);
             burst(v, buf, lc);
-            efo_blit(v, strips, buf + v->active_start + 16, i - top, 0, 352, frame_counter);
+            uint16_t* dst = buf + v->active_start + 16;
+            const uint8_t* f = strips_a; const uint8_t* g = strips_b;
+            int h = hscroll;
+            if (h < 0) { h += 352; f = strips_b; g = strips_a; }       /* video.cpp:1148-1151 */
+            efo_blit(v, f, dst, i - top, h, 352 - h, frame_counter);
+            if (h) efo_blit(v, g, dst + (352 - h) * 2, i - top, 0, h, frame_counter);
         } else if (i >= vsync_start) {
             if (!v->ntsc) {
                 uint8_t t = sync_type[i - 304];
                 pal_sync_half(v, buf, v->line_width / 2, t & 2);
                 pal_sync_half(v, buf + v->line_width / 2, v->line_width / 2, t & 1);
             } else blanking(v, buf, 1, lc);
-        } else blanking(v, buf, 0, lc);
+        } else {
+            blanking(v, buf, 0, lc);
+            int ptop = bottom + 2;
+            if (i >= ptop && i < ptop + 16) overlay(v, buf + v->active_start + 16, i - ptop, bitmap, blend, progress);
+        }
         memcpy(out + (size_t)i * v->line_width, buf, (size_t)v->line_width * 2);
     }
     free(lb[0]); free(lb[1]);
+}
+
+void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uint16_t* out)
+{
+    efo_field_ex(v, strips, strips, frame_counter, 0, NULL, 0, 0, out);
 }

@@ -74,6 +74,12 @@ void efo_blit(const efo_video* v, const uint8_t* strips, uint16_t* dst, int line
  * no overlay); out = line_count x line_width uint16 */
 void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uint16_t* out);
 
+/* the same with video_isr's presentation extras: hscroll (video.cpp:1146-1154; strips_b = the other
+ * frame store) and the 80x16 overlay bitmap + progress bar of composite() (video.cpp:845-887);
+ * blend 0 = off, -1 or >= 32 = full, 1..31 = fading; bitmap may be NULL when blend == 0 */
+void efo_field_ex(const efo_video* v, const uint8_t* strips_a, const uint8_t* strips_b, int frame_counter, int hscroll,
+                  const uint8_t* bitmap, int blend, int progress, uint16_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,30 @@ long efref_field(const uint8_t* i420, const uint8_t* i420_b, int frame_counter, 
     return (long)lines * w;
 }
 
+// Whole field with the presentation extras of video_isr: two-frame horizontal scroll (_hscroll,
+// video.cpp:1146-1154) and the time/progress overlay composite() (video.cpp:845-887).
+long efref_field_ex(const uint8_t* i420, const uint8_t* i420_b, int frame_counter, int hscroll,
+                    const uint8_t* bitmap, int blend, int progress, uint16_t* out)
+{
+    load_i420(&g_fb[0], i420);
+    if (i420_b) load_i420(&g_fb[1], i420_b);
+    _frames = g_fb; _current_frame = 0; _next_frame = -1;
+    _line_counter = 0; _frame_counter = frame_counter; _hscroll = (int16_t)hscroll;
+    if (bitmap) memcpy(_video_composite, bitmap, VIDEO_COMPOSITE_WIDTH * VIDEO_COMPOSITE_HEIGHT);
+    _video_composite_blend = blend; _video_composite_progress = progress;
+    uint16_t* lb[2];
+    lb[0] = (uint16_t*)calloc(_line_width + 64, 2);
+    lb[1] = (uint16_t*)calloc(_line_width + 64, 2);
+    int lines = _line_count, w = _line_width;
+    for (int l = 0; l < lines; l++) {
+        video_isr(lb[l & 1]);
+        memcpy(out + (size_t)l * w, lb[l & 1], (size_t)w * 2);
+    }
+    free(lb[0]); free(lb[1]);
+    _video_composite_blend = 0; _hscroll = 0;
+    return (long)lines * w;
+}
+
 // One blit() call (video.cpp:690) into a caller buffer: the north_star "line-blit entry point".
 void efref_blit(const uint8_t* i420, int frame_counter, uint16_t* dst, int line, int x, int width)
 {

@@ -44,6 +44,7 @@ class Oracle:
         L.efo_video_init.argtypes = [VP, ctypes.c_int]
         L.efo_blit.argtypes = [VP, VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.efo_field.argtypes = [VP, VP, ctypes.c_int, VP]
+        L.efo_field_ex.argtypes = [VP, VP, VP, ctypes.c_int, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, VP]
         L.efo_stats_get.argtypes = [VP]
         self._video = {}
 
@@ -98,6 +99,15 @@ class Oracle:
         self.lib.efo_field(ctypes.byref(v), strips.ctypes.data, frame_counter, out.ctypes.data)
         return out
 
+    def field_ex(self, i420_a, i420_b, ntsc, frame_counter, hscroll=0, bitmap=None, blend=0, progress=0):
+        v = self.video(ntsc)
+        sa, sb = self.i420_to_strips(i420_a), self.i420_to_strips(i420_b)
+        out = np.zeros(v.line_width * v.line_count, dtype=np.uint16)
+        bm = None if bitmap is None else np.ascontiguousarray(bitmap, dtype=np.uint8)
+        self.lib.efo_field_ex(ctypes.byref(v), sa.ctypes.data, sb.ctypes.data, frame_counter, hscroll,
+                              None if bm is None else bm.ctypes.data, blend, progress, out.ctypes.data)
+        return out
+
     def blit(self, i420, ntsc, line, x, width, frame_counter):
         v = self.video(ntsc)
         strips = self.i420_to_strips(i420)
@@ -139,6 +149,8 @@ class RefVideo:
         self.lib.efref_field.restype = ctypes.c_long
         self.lib.efref_field.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int, VP]
         self.lib.efref_blit.argtypes = [VP, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        self.lib.efref_field_ex.restype = ctypes.c_long
+        self.lib.efref_field_ex.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, VP]
         self.std = None
 
     def init(self, ntsc):
@@ -154,6 +166,15 @@ class RefVideo:
         i420 = np.ascontiguousarray(i420, dtype=np.uint8)
         out = np.zeros(g[0] * g[1], dtype=np.uint16)
         self.lib.efref_field(i420.ctypes.data, None, frame_counter, 0, out.ctypes.data)
+        return out
+
+    def field_ex(self, i420_a, i420_b, ntsc, frame_counter, hscroll=0, bitmap=None, blend=0, progress=0):
+        g = self.init(ntsc)
+        a = np.ascontiguousarray(i420_a, dtype=np.uint8)
+        b = np.ascontiguousarray(i420_b, dtype=np.uint8)
+        bm = None if bitmap is None else np.ascontiguousarray(bitmap, dtype=np.uint8)
+        out = np.zeros(g[0] * g[1], dtype=np.uint16)
+        self.lib.efref_field_ex(a.ctypes.data, b.ctypes.data, frame_counter, hscroll, None if bm is None else bm.ctypes.data, blend, progress, out.ctypes.data)
         return out
 
     def blit(self, i420, ntsc, line, x, width, frame_counter):

@@ -77,3 +77,26 @@ def test_decode_then_composite_latest_frame(oracle):
     c.composite_field(fb=-1, frame_counter=2)
     assert np.array_equal(c.read_field(0), oracle.field(frames[2], 1, 2))
     c.close()
+
+
+def test_scroll_and_overlay(oracle):
+    """video_isr's two-frame scroll (_hscroll) and the composite() overlay, sample-exact."""
+    rng = np.random.default_rng(12)
+    a, b = rng.integers(0, 249, 101376, dtype=np.uint8), rng.integers(0, 249, 101376, dtype=np.uint8)
+    bm = rng.integers(0, 256, 1280, dtype=np.uint8)
+    c = espflix_b200.Context(n_streams=2, max_pictures=2, es_capacity=4096, fields=True)
+    c.write_frame_i420(1, 0, a)
+    c.write_frame_i420(1, 1, b)
+    cases = [(0, 0, 0), (8, 0, 0), (-8, 0, 0), (176, 0, 0), (-344, 0, 0), (344, -1, 100), (0, 32, 0), (0, 5, 239), (0, 31, 17), (24, 1, 300)]
+    for ntsc in (1, 0):
+        c.video_init(ntsc)
+        for hs, blend, prog in cases:
+            c.set_scroll(hs)
+            c.set_overlay(bm, blend, prog)
+            c.composite_field(fb=0, frame_counter=1)
+            got, want = c.read_field(1), oracle.field_ex(a, b, ntsc, 1, hs, bm, blend, prog)
+            d = np.nonzero(got != want)[0]
+            assert d.size == 0, "std %d hscroll %d blend %d progress %d: %d samples differ, first at %d" % (ntsc, hs, blend, prog, d.size, d[0])
+    with pytest.raises(espflix_b200.EspflixError):
+        c.set_scroll(12)
+    c.close()

@@ -54,3 +54,18 @@ def test_reference_video_equals_port_on_random_frames(oracle):
         assert np.array_equal(oracle.field(fr, ntsc, 1), rv.field(fr, ntsc, 1))
         for line, x, w in ((0, 0, 352), (191, 0, 352), (77, 16, 64), (100, 8, 344)):
             assert np.array_equal(oracle.blit(fr, ntsc, line, x, w, 1), rv.blit(fr, ntsc, line, x, w, 1)), (ntsc, line, x, w)
+
+
+PRESENTATION_CASES = [(0, 0, 0), (8, 0, 0), (-8, 0, 0), (176, 0, 0), (-344, 0, 0), (344, -1, 100), (0, 32, 0), (0, 5, 239), (0, 31, 17), (24, 1, 300)]
+
+
+def test_presentation_extras_port_equals_reference(oracle):
+    """_hscroll two-frame scroll and the composite() overlay / progress bar / fade."""
+    rv = oracle_lib.RefVideo()
+    rng = np.random.default_rng(11)
+    a, b = rng.integers(0, 249, 101376, dtype=np.uint8), rng.integers(0, 249, 101376, dtype=np.uint8)
+    bm = rng.integers(0, 256, 1280, dtype=np.uint8)
+    for ntsc in (1, 0):
+        for hs, blend, prog in PRESENTATION_CASES:
+            want = rv.field_ex(a, b, ntsc, 1, hs, bm, blend, prog)
+            assert np.array_equal(oracle.field_ex(a, b, ntsc, 1, hs, bm, blend, prog), want), (ntsc, hs, blend, prog)
