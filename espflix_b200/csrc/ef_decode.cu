@@ -147,7 +147,7 @@ __device__ __forceinline__ void idct8(int (&v)[8])
     int t2 = v[3] + v[5];
     int b6 = v[1] - v[7];
     int b7 = t1 + t2;
-    int m0 = v[0];
+    int m0 = kFinal ? v[0] + 128 : v[0];            // every output carries m0 exactly once: the final (x + 128) >> 8 needs one add
     int x4 = ((b6 * 473 - b4 * 196 + 128) >> 8) - b7;
     int x0 = x4 - (((t1 - t2) * 362 + 128) >> 8);
     int x1 = m0 - b1;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void idct8(int (&v)[8])
     v[4] = y6 + y7; v[5] = x0 + y5; v[6] = y3 - x4; v[7] = y4 - b7;
     if (kFinal) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = (v[i] + 128) >> 8;
+        for (int i = 0; i < 8; i++) v[i] >>= 8;
     }
 }
 
@@ -177,7 +177,8 @@ __device__ __forceinline__ int dequant(int level, int intra, int qsq)
 __device__ __forceinline__ uint32_t pin4(uint32_t pred, int r0, int r1, int r2, int r3)
 {
     // PIN(b + s) for four pixels (add_block, player.cpp:1189; _pin clamps to [0,248], Q1):
-    // max(min(pred + res, 248), 0) is one DPX instruction per pixel
+    // max(min(pred + res, 248), 0) is one DPX instruction per pixel. (The packed s16x2 form would
+    // halve this but its 16-bit add could wrap for residuals beyond +-32,512; kept exact for any int.)
     const int p0 = __viaddmin_s32_relu((int)(pred & 0xFF), r0, 248);
     const int p1 = __viaddmin_s32_relu((int)((pred >> 8) & 0xFF), r1, 248);
     const int p2 = __viaddmin_s32_relu((int)((pred >> 16) & 0xFF), r2, 248);
