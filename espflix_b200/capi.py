@@ -50,6 +50,8 @@ _SIGNATURES = {
     "ef_write_frame": (_I, [_VP, _I, _I, _VP]),
     "ef_frame_device_ptr": (_I, [_VP, _I, _I, ctypes.POINTER(_VP)]),
     "ef_read_latest_i420": (_I, [_VP, _I, _I, _VP, _VP]),
+    "ef_read_latest_i420_async": (_I, [_VP, _I, _I, _VP, _VP]),
+    "ef_sync": (_I, [_VP, _VP]),
     "ef_video_init": (_I, [_VP, _I]),
     "ef_video_geometry": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "ef_composite_field": (_I, [_VP, _I, _I, _VP]),
@@ -175,6 +177,12 @@ class Context:
             out = np.empty((count, I420_BYTES), dtype=np.uint8)
         self._check(self.lib.ef_read_latest_i420(self._h, first, count, _ptr(out), stream))
         return out
+
+    def read_latest_i420_async(self, first, count, out, stream=0):
+        self._check(self.lib.ef_read_latest_i420_async(self._h, first, count, _ptr(out), stream))
+
+    def sync(self, stream=0):
+        self._check(self.lib.ef_sync(self._h, stream))
 
     def frame_device_ptr(self, s, fb):
         p = _VP()

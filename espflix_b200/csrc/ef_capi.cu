@@ -92,10 +92,21 @@ struct ef_ctx {
     ef_config cfg;
     int sm_count = 0;
     EfDev h;                   // host copy of the device context
-    EfDev* d = nullptr;
+    EfDev* d = nullptr;           // = dd[active]
     std::vector<void*> allocs;
-    uint8_t* d_es = nullptr;  // owned ES buffer (es_capacity + 64)
-    uint64_t* d_es_off = nullptr;
+    // Two elementary-stream buffers: a submit uploads into the back one on an internal stream while
+    // the kernels of the previous submit still read the front one; ef_index flips them.
+    uint8_t* d_es2[2] = { nullptr, nullptr };
+    uint64_t* d_es_off2[2] = { nullptr, nullptr };
+    EfDev* dd[2] = { nullptr, nullptr };          // device copies of `h`, one per ES buffer
+    uint64_t* h_off[2] = { nullptr, nullptr };    // pinned copies of the offsets of the submit in flight
+    int active = 0, pending = -1;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t ev_user = nullptr, ev_up_done[2] = { nullptr, nullptr }, ev_buf_free[2] = { nullptr, nullptr };
+    cudaEvent_t ev_export = nullptr, ev_down_done[2] = { nullptr, nullptr };
+    uint8_t* d_stage2[2] = { nullptr, nullptr };  // read-back staging of ef_read_latest_i420(_async), alternating
+    size_t stage2_bytes[2] = { 0, 0 };
+    int stage_idx = 0;
     uint8_t* d_ts = nullptr;  // TS staging (same capacity) + packet tables, allocated on first TS submit
     uint32_t* d_pkt_len = nullptr;
     uint64_t* d_pkt_off = nullptr;
@@ -122,6 +133,17 @@ int dev_alloc(ef_ctx* c, T** p, size_t n)
     if (e != cudaSuccess) return fail(EF_ECUDA, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
     c->allocs.push_back(v);
     *p = (T*)v;
+    return EF_OK;
+}
+
+// write the host copy of the device context to both device copies (they differ in the ES buffer only)
+int push_dev(ef_ctx* c)
+{
+    for (int b = 0; b < 2; b++) {
+        EfDev t = c->h;
+        t.es = c->d_es2[b]; t.es_off = c->d_es_off2[b];
+        CK(cudaMemcpy(c->dd[b], &t, sizeof(EfDev), cudaMemcpyHostToDevice));
+    }
     return EF_OK;
 }
 
@@ -185,8 +207,19 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     h.max_seq = cfg->max_pictures;
     int rc;
 #define A(ptr, count) if ((rc = dev_alloc(c, &(ptr), (count))) != EF_OK) { ef_destroy(c); return rc; }
-    A(c->d_es, cfg->es_capacity + 1024);
-    A(c->d_es_off, (size_t)n + 1);
+    for (int b = 0; b < 2; b++) {
+        A(c->d_es2[b], cfg->es_capacity + 1024);
+        A(c->d_es_off2[b], (size_t)n + 1);
+        A(c->dd[b], 1);
+        CK(cudaHostAlloc((void**)&c->h_off[b], ((size_t)n + 1) * 8, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&c->ev_up_done[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_buf_free[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_down_done[b], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_export, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
     A(h.frames, (size_t)n * 2 * EF_FRAME + 1024);
     A(h.seq, (size_t)n * (h.max_seq + 1));
     A(h.pics, (size_t)n * h.max_pictures);
@@ -203,9 +236,9 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     A(c->d_color_tab, 768); A(c->d_pal_burst, 128); A(c->d_default_intra, 64); A(c->d_overlay, 1280);
     c->present.bitmap = c->d_overlay;
     if (cfg->fields) { h.field_stride = EF_PAL_FIELD_SAMPLES; A(h.fields, (size_t)n * h.field_stride); }
-    A(c->d, 1);
 #undef A
-    h.es = c->d_es; h.es_off = c->d_es_off; h.tables = dt;
+    h.es = c->d_es2[0]; h.es_off = c->d_es_off2[0]; h.tables = dt;
+    c->d = c->dd[0];
     h.color_tab = c->d_color_tab; h.pal_burst = c->d_pal_burst;
 
     EfTables t;
@@ -213,10 +246,12 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     if (bad) { ef_destroy(c); return fail(EF_EINVAL, "internal: VLC table %d does not fit its lookup shape", bad); }
     CK(cudaMemcpy(dt, &t, sizeof(t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_default_intra, ef_default_intra_ptr(), 64, cudaMemcpyHostToDevice));
-    CK(cudaMemset(c->d_es, 0, cfg->es_capacity + 1024));
-    CK(cudaMemset(c->d_es_off, 0, ((size_t)n + 1) * 8));
+    for (int b = 0; b < 2; b++) {
+        CK(cudaMemset(c->d_es2[b], 0, cfg->es_capacity + 1024));
+        CK(cudaMemset(c->d_es_off2[b], 0, ((size_t)n + 1) * 8));
+    }
     CK(cudaMemset(c->d_overlay, 0, 1280));
-    CK(cudaMemcpy(c->d, &h, sizeof(h), cudaMemcpyHostToDevice));
+    { int rcp = push_dev(c); if (rcp != EF_OK) { ef_destroy(c); return rcp; } }
     *out = c;
     rc = ef_reset(c);
     if (rc != EF_OK) { ef_destroy(c); *out = nullptr; return rc; }
@@ -230,6 +265,16 @@ void ef_destroy(ef_ctx* c)
     if (!c) return;
     cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
+    for (int b = 0; b < 2; b++) {
+        if (c->h_off[b]) cudaFreeHost(c->h_off[b]);
+        if (c->ev_up_done[b]) cudaEventDestroy(c->ev_up_done[b]);
+        if (c->ev_buf_free[b]) cudaEventDestroy(c->ev_buf_free[b]);
+        if (c->ev_down_done[b]) cudaEventDestroy(c->ev_down_done[b]);
+    }
+    if (c->ev_user) cudaEventDestroy(c->ev_user);
+    if (c->ev_export) cudaEventDestroy(c->ev_export);
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
+    if (c->down_stream) cudaStreamDestroy(c->down_stream);
     delete c;
 }
 
@@ -242,29 +287,41 @@ int ef_reset(ef_ctx* c)
     c->launches++;
     CK(cudaMemset(c->h.info, 0, 32));
     CK(cudaDeviceSynchronize());
-    c->indexed = false; c->submitted = false;
+    c->indexed = false; c->submitted = false; c->pending = -1;
     return EF_OK;
 }
 
+// Uploads go to the BACK elementary-stream buffer on the context's own upload stream, so that a
+// caller that has pinned its input can submit batch k+1 while the kernels of batch k still run
+// (the producer side of the reference's Buffer queue is asynchronous in the same way). ef_index()
+// makes the compute stream wait for the upload and flips the buffers.
 static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, bool host, bool ts, cudaStream_t st)
 {
     if (!c || !src || !off) return fail(EF_EINVAL, "null argument");
     const int n = c->cfg.n_streams;
-    std::vector<uint64_t> hoff((size_t)n + 1);
-    if (host) memcpy(hoff.data(), off, ((size_t)n + 1) * 8);
-    else { CK(cudaMemcpyAsync(hoff.data(), off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    const int b = c->pending >= 0 ? c->pending : (c->active ^ 1);
+    CK(cudaEventSynchronize(c->ev_up_done[b]));          // the pinned offsets of the previous upload into this buffer are free again
+    uint64_t* hoff = c->h_off[b];
+    if (host) memcpy(hoff, off, ((size_t)n + 1) * 8);
+    else { CK(cudaMemcpyAsync(hoff, off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
     const uint64_t total = hoff[n];
     if (total > c->cfg.es_capacity) return fail(EF_ENOMEM, "submit of %llu bytes exceeds es_capacity %zu", (unsigned long long)total, c->cfg.es_capacity);
     for (int i = 0; i < n; i++) if (hoff[i] > hoff[i + 1]) return fail(EF_EINVAL, "stream offsets must be non-decreasing");
+    if (ts) for (int i = 0; i <= n; i++) if (hoff[i] % 188) return fail(EF_EINVAL, "TS stream offsets must be multiples of 188");
     const cudaMemcpyKind kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    cudaStream_t up = c->up_stream;
+    if (!host) {                                          // device-resident input may still be in production on the caller's stream
+        CK(cudaEventRecord(c->ev_user, st));
+        CK(cudaStreamWaitEvent(up, c->ev_user, 0));
+    }
+    CK(cudaStreamWaitEvent(up, c->ev_buf_free[b], 0));    // kernels of the submit that last used this buffer are done
+    uint8_t* d_es = c->d_es2[b];
+    uint64_t* d_es_off = c->d_es_off2[b];
     if (!ts) {
-        CK(cudaMemcpyAsync(c->d_es, src, total, kind, st));
-        CK(cudaMemsetAsync(c->d_es + total, 0, 256, st));
-        CK(cudaMemcpyAsync(c->d_es_off, hoff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));          // hoff is a local
-        c->es_bytes = total;
+        CK(cudaMemcpyAsync(d_es, src, total, kind, up));
+        CK(cudaMemsetAsync(d_es + total, 0, 256, up));
+        CK(cudaMemcpyAsync(d_es_off, hoff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, up));
     } else {
-        for (int i = 0; i <= n; i++) if (hoff[i] % 188) return fail(EF_EINVAL, "TS stream offsets must be multiples of 188");
         const uint64_t n_packets = total / 188;
         if (!c->d_ts) {
             int rc;
@@ -273,20 +330,21 @@ static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, boo
             if ((rc = dev_alloc(c, &c->d_pkt_off, c->cfg.es_capacity / 188 + 1)) != EF_OK) return rc;
             if ((rc = dev_alloc(c, &c->d_ts_off, (size_t)n + 1)) != EF_OK) return rc;
         }
-        CK(cudaMemcpyAsync(c->d_ts, src, total, kind, st));
-        CK(cudaMemcpyAsync(c->d_ts_off, hoff.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_ts, src, total, kind, up));
+        CK(cudaMemcpyAsync(c->d_ts_off, hoff, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, up));
         if (n_packets) {
-            ef_ts_len_kernel<<<(unsigned)((n_packets + 255) / 256), 256, 0, st>>>(c->d_ts, n_packets, c->d_pkt_len);
+            ef_ts_len_kernel<<<(unsigned)((n_packets + 255) / 256), 256, 0, up>>>(c->d_ts, n_packets, c->d_pkt_len);
             CK(cudaGetLastError());
-            ef_ts_scan_kernel<<<1, 1024, 0, st>>>(c->d_pkt_len, n_packets, c->d_pkt_off, c->d_ts_off, n, c->d_es_off, c->d_es);
+            ef_ts_scan_kernel<<<1, 1024, 0, up>>>(c->d_pkt_len, n_packets, c->d_pkt_off, c->d_ts_off, n, d_es_off, d_es);
             CK(cudaGetLastError());
-            ef_ts_copy_kernel<<<(unsigned)((n_packets * 32 + 255) / 256), 256, 0, st>>>(c->d_ts, n_packets, c->d_pkt_off, c->d_es);
+            ef_ts_copy_kernel<<<(unsigned)((n_packets * 32 + 255) / 256), 256, 0, up>>>(c->d_ts, n_packets, c->d_pkt_off, d_es);
             CK(cudaGetLastError());
             c->launches += 3;
-        } else CK(cudaMemsetAsync(c->d_es_off, 0, ((size_t)n + 1) * 8, st));
-        CK(cudaStreamSynchronize(st));
-        c->es_bytes = total;                    // upper bound; exact ES size is on the device
+        } else CK(cudaMemsetAsync(d_es_off, 0, ((size_t)n + 1) * 8, up));
     }
+    CK(cudaEventRecord(c->ev_up_done[b], up));
+    c->es_bytes = total;                        // for TS input an upper bound; the exact ES size is on the device
+    c->pending = b;
     c->submitted = true; c->indexed = false;
     return EF_OK;
 }
@@ -302,6 +360,11 @@ int ef_index(ef_ctx* c, void* stream)
     if (!c->submitted) return fail(EF_ESTATE, "ef_index before any submit");
     cudaStream_t st = (cudaStream_t)stream;
     const int n = c->cfg.n_streams;
+    if (c->pending >= 0) {                       // a fresh submit: wait for its upload, make it the front buffer
+        CK(cudaStreamWaitEvent(st, c->ev_up_done[c->pending], 0));
+        c->active = c->pending; c->pending = -1;
+        c->d = c->dd[c->active];
+    }                                            // else: index the front buffer again (same input, next GOP period)
     CK(cudaMemsetAsync(c->h.info, 0, 32, st));
     ef_scan_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(c->d);
     CK(cudaGetLastError());
@@ -311,6 +374,7 @@ int ef_index(ef_ctx* c, void* stream)
     ef_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->d);
     CK(cudaGetLastError());
     c->launches += 3;
+    CK(cudaEventRecord(c->ev_buf_free[c->active], st));
     c->indexed = true;
     return EF_OK;
 }
@@ -327,7 +391,7 @@ int ef_index_info(ef_ctx* c, int* max_pictures, uint64_t* total_pictures, uint64
     if (total_slices) *total_slices = info[2];
     if (es_bytes) {
         uint64_t last = 0;
-        CK(cudaMemcpy(&last, c->d_es_off + c->cfg.n_streams, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&last, c->d_es_off2[c->active] + c->cfg.n_streams, 8, cudaMemcpyDeviceToHost));
         *es_bytes = last;
     }
     if (info[3]) return fail(EF_ENOMEM, "index overflow (flags %u): raise max_pictures / max_slices_per_picture", info[3]);
@@ -352,6 +416,7 @@ int ef_decode_picture(ef_ctx* c, int pic, void* stream)
     if (!c->indexed) return fail(EF_ESTATE, "ef_decode_picture before ef_index");
     if (pic < 0 || pic >= c->cfg.max_pictures) return fail(EF_EINVAL, "picture index %d out of range", pic);
     CK(ef_launch_decode(c->d, pic, c->sm_count, (cudaStream_t)stream));
+    CK(cudaEventRecord(c->ev_buf_free[c->active], (cudaStream_t)stream));     // the front ES buffer is in use until here
     c->launches++;
     return EF_OK;
 }
@@ -382,19 +447,46 @@ int ef_read_frame(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
     return EF_OK;
 }
 
-int ef_read_latest_i420(ef_ctx* c, int first, int count, uint8_t* dst, void* stream)
+int ef_read_latest_i420_async(ef_ctx* c, int first, int count, uint8_t* dst, void* stream)
 {
     if (!c || !dst) return fail(EF_EINVAL, "null argument");
     if (first < 0 || count < 1 || first + count > c->cfg.n_streams) return fail(EF_EINVAL, "stream range out of bounds");
-    int rc = ensure_stage(c, (size_t)count * EF_FRAME);
-    if (rc != EF_OK) return rc;
+    const int k = c->stage_idx ^= 1;
+    const size_t bytes = (size_t)count * EF_FRAME;
+    if (c->stage2_bytes[k] < bytes) {
+        CK(cudaEventSynchronize(c->ev_down_done[k]));
+        void* v = nullptr;
+        CK(cudaMalloc(&v, bytes));
+        c->allocs.push_back(v);
+        c->d_stage2[k] = (uint8_t*)v; c->stage2_bytes[k] = bytes;
+    }
     cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaStreamWaitEvent(st, c->ev_down_done[k], 0));        // the previous copy out of this staging buffer has finished
     const uint64_t threads = (uint64_t)count * (EF_FRAME / 4);
-    ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, 0, c->d_stage);
+    ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, 0, c->d_stage2[k]);
     CK(cudaGetLastError());
     c->launches++;
-    CK(cudaMemcpyAsync(dst, c->d_stage, (size_t)count * EF_FRAME, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(c->ev_export, st));
+    CK(cudaStreamWaitEvent(c->down_stream, c->ev_export, 0));
+    CK(cudaMemcpyAsync(dst, c->d_stage2[k], bytes, cudaMemcpyDeviceToHost, c->down_stream));   // overlaps the next decode when dst is pinned
+    CK(cudaEventRecord(c->ev_down_done[k], c->down_stream));
+    return EF_OK;
+}
+
+int ef_sync(ef_ctx* c, void* stream)
+{
+    if (!c) return fail(EF_EINVAL, "null context");
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaStreamSynchronize(c->up_stream));
+    CK(cudaStreamSynchronize(c->down_stream));
+    return EF_OK;
+}
+
+int ef_read_latest_i420(ef_ctx* c, int first, int count, uint8_t* dst, void* stream)
+{
+    int rc = ef_read_latest_i420_async(c, first, count, dst, stream);
+    if (rc != EF_OK) return rc;
+    CK(cudaStreamSynchronize(c->down_stream));
     return EF_OK;
 }
 
@@ -473,7 +565,7 @@ int ef_video_init(ef_ctx* c, int ntsc)
     CK(cudaMemcpy(c->d_color_tab, tab, sizeof(tab), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_pal_burst, burst, sizeof(burst), cudaMemcpyHostToDevice));
     c->h.geo = g;
-    CK(cudaMemcpy(c->d, &c->h, sizeof(EfDev), cudaMemcpyHostToDevice));
+    { int rcp = push_dev(c); if (rcp != EF_OK) return rcp; }
     c->video = true;
     return EF_OK;
 }

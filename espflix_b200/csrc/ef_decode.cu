@@ -438,15 +438,27 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     SliceState s;
     s.first = 0; s.cur = nullptr; s.ref = nullptr; s.qtab = T.qdef; s.mbw = 0;
     bool active = false, exhausted = false;
+    // First round: slices are dealt out statically, 32 consecutive ones per warp, warps interleaved across
+    // the SMs - with fewer slices than lanes (4,096 pictures x 12 slices vs 71 K lanes) every SM then runs
+    // the same number of full warps instead of whichever warps reach the cursor first. Later rounds (lanes
+    // whose slice ended) pull from the global cursor, which counts from the end of the first round.
+    const uint32_t first_round = gridDim.x * (uint32_t)kWarpsPerCta * 32u;
+    bool first_fill = true;
 
     for (;;) {
         // ---- refill idle lanes with new slices -------------------------------------------------
         unsigned need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
         if (need) {
-            uint32_t base = 0;
-            int leader = __ffs(need) - 1;
-            if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(need));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            uint32_t base;
+            if (first_fill) {
+                base = ((uint32_t)warp * gridDim.x + blockIdx.x) * 32u;
+                first_fill = false;
+            } else {
+                base = 0;
+                int leader = __ffs(need) - 1;
+                if (lane == leader) base = first_round + atomicAdd(cursor, (uint32_t)__popc(need));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            }
             if (!active && !exhausted) {
                 uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1));
                 if (idx >= total) exhausted = true;

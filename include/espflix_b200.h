@@ -78,7 +78,10 @@ int ef_reset(ef_ctx* ctx);      /* zero frame stores, picture counters and seque
 /* Submit one batch. es/ts = all streams back to back; off[n_streams+1] = byte offsets of each
  * stream in it. The *_host forms copy from (pinned or pageable) host memory; *_device forms take
  * device pointers (inputs already resident in HBM). `stream` is a cudaStream_t (0 = default).
- * Each submit must hold whole pictures (cut at picture/sequence start codes). */
+ * Each submit must hold whole pictures (cut at picture/sequence start codes). A submit is queued on an
+ * internal upload stream into the back one of two device buffers and returns at once when the input is
+ * pinned (or device) memory, so batch k+1 can be submitted while batch k is still being decoded; the
+ * next ef_index() orders the compute stream after the upload. */
 int ef_submit_es_host(ef_ctx* ctx, const uint8_t* es, const uint64_t* off, void* stream);
 int ef_submit_es_device(ef_ctx* ctx, const uint8_t* es, const uint64_t* off, void* stream);
 int ef_submit_ts_host(ef_ctx* ctx, const uint8_t* ts, const uint64_t* off, void* stream);
@@ -105,8 +108,13 @@ int ef_write_frame(ef_ctx* ctx, int stream_index, int fb, const uint8_t* src_str
 /* Device address of a stream's frame store (for zero-copy consumers; macroblock-tiled: tile (mx,my) at
  * (my*22+mx)*384 = Y[16][16], block-4 chroma [8][8], block-5 chroma [8][8]); fb as above but not -1. */
 int ef_frame_device_ptr(ef_ctx* ctx, int stream_index, int fb, void** ptr);
-/* Batched read-back of the most recent picture of streams [first, first+count) as I420. */
+/* Batched read-back of the most recent picture of streams [first, first+count) as I420. The _async form
+ * returns once the copy is queued (dst should be pinned; it is complete after ef_sync) so that it overlaps
+ * the next submit/decode; the plain form waits for it. */
 int ef_read_latest_i420(ef_ctx* ctx, int first, int count, uint8_t* dst, void* stream);
+int ef_read_latest_i420_async(ef_ctx* ctx, int first, int count, uint8_t* dst, void* stream);
+/* Wait for `stream` and for the context's internal upload / read-back streams. */
+int ef_sync(ef_ctx* ctx, void* stream);
 
 /* K2: composite synthesis. */
 int ef_video_init(ef_ctx* ctx, int ntsc);                          /* 1 NTSC, 0 PAL */

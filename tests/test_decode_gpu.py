@@ -149,3 +149,22 @@ def test_error_paths():
         small.index_info()                                              # 4 pictures > max_pictures 2
     small.close()
     ctx.close()
+
+
+def test_pipelined_submits_and_async_readback(oracle):
+    """Submit batch k+1 while batch k is still in flight, read back asynchronously: results must equal
+    the plain synchronous sequence (double-buffered ES upload and read-back staging in the C-ABI)."""
+    batches = [[synth.generate(synth.SEED0 + 300 + 7 * b + i, n_pictures=6, gop=6)[0] for i in range(5)] for b in range(4)]
+    ctx = espflix_b200.Context(n_streams=5, max_pictures=6, es_capacity=1 << 21, fields=False)
+    outs = [np.zeros((5, 101376), dtype=np.uint8) for _ in batches]
+    packed = [ctx.pack(b) for b in batches]
+    for k, (blob, off) in enumerate(packed):
+        ctx.submit_es(blob, off)
+        ctx.index()
+        ctx.decode_all(6)
+        ctx.read_latest_i420_async(0, 5, outs[k])
+    ctx.sync()
+    for k, b in enumerate(batches):
+        for i, es in enumerate(b):
+            assert np.array_equal(outs[k][i], oracle.decode_es(es)[-1]), (k, i)
+    ctx.close()
