@@ -179,7 +179,8 @@ const char* ef_version(void) { return "espflix_b200 0.1 (sm_100a)"; }
 int ef_create(ef_ctx** out, const ef_config* cfg)
 {
     if (!out || !cfg) return fail(EF_EINVAL, "null argument");
-    if (cfg->n_streams < 1 || cfg->max_pictures < 1 || cfg->max_slices_per_picture < 1 || cfg->es_capacity < 16)
+    if (cfg->n_streams < 1 || cfg->n_streams > 65535 || cfg->max_pictures < 1 || cfg->max_pictures > 4096 ||
+        cfg->max_slices_per_picture < 1 || cfg->max_slices_per_picture > 176 || cfg->es_capacity < 16)
         return fail(EF_EINVAL, "bad config (n_streams=%d max_pictures=%d max_slices_per_picture=%d es_capacity=%zu)",
                     cfg->n_streams, cfg->max_pictures, cfg->max_slices_per_picture, cfg->es_capacity);
     int ndev = 0;

@@ -61,7 +61,7 @@ typedef struct ef_ctx ef_ctx;
 
 typedef struct {
     int device;                 /* CUDA device ordinal */
-    int n_streams;              /* independent decoders in this context */
+    int n_streams;              /* independent decoders in this context (1..65535) */
     int max_pictures;           /* per stream per submit */
     int max_slices_per_picture; /* per stream (reference accepts slice codes 1..12) */
     size_t es_capacity;         /* bytes of elementary stream per submit, whole batch */
