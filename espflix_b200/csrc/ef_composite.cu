@@ -16,7 +16,7 @@ namespace {
 
 __device__ __forceinline__ uint32_t chroma_word(const uint32_t* tab, uint32_t u, uint32_t v, int vt)
 {
-    return ((__ldg(tab + (u & 255)) + __ldg(tab + vt + (v & 255))) & 0xFCFCFCFCu) >> 2;      // CHROMA_EVEN / CHROMA_ODD, video.cpp:670
+    return ((tab[u & 255] + tab[vt + (v & 255)]) & 0xFCFCFCFCu) >> 2;      // CHROMA_EVEN / CHROMA_ODD, video.cpp:670
 }
 
 // compile-time geometry of the two standards (video_init / pal_init, video.cpp:572-630; values
@@ -60,100 +60,128 @@ __constant__ uint32_t c_dither[8] = {                                     // dit
 
 }  // namespace
 
-// grid: x = threads of one field / 256, y = stream. A warp covers 16 consecutive 16-byte chunks of TWO
-// consecutive lines (lanes 0-15 the even line, lanes 16-31 the odd one): in the tiled frame the two luma
-// rows of a tile share 32-byte sectors and both lines read the same chroma row, so every sector the warp
-// fetches is used whole. Stores stay 256 contiguous bytes per half-warp.
+// eight samples (one 16-byte chunk) of a blank / vsync line, or of an active line outside the blit span
+// (which still shows what blanking() last left in the ping-pong buffer: sync, burst, BLACK). Most chunks lie
+// wholly inside one constant region: decide per chunk, go per sample only at the burst, on the vsync lines
+// and under the overlay.
+template <bool kNtsc>
+__device__ __forceinline__ uint4 blank_chunk(const EfDev& D, const EfPresent& pr, int line, int x0)
+{
+    using G = Geo<kNtsc>;
+    const uint32_t SYNC2 = 0x00000000u, BLACK2 = 0x18001800u;
+    uint32_t w[4];
+    const int ol = line - (G::TOP + EF_H + 2);                             // overlay line 0..15 (video.cpp:1183-1189)
+    if (pr.blend != 0 && ol >= 0 && ol < 16 && x0 >= G::BLIT + 16 && x0 < G::BLIT + 16 + 160 + 16 + 480) {
+        // composite(), video.cpp:845-887: 80 bitmap bytes -> 160 samples, then (lines 3..8) a 480-sample progress bar
+        int scale = 255 / 4;
+        if (pr.blend != -1 && pr.blend < 32) scale = (scale * pr.blend) >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int s = x0 + 2 * i - (G::BLIT + 16);                     // both samples of a word share the source byte / bar step
+            uint32_t v = 0x1800u;
+            if (s < 160) v = 0x1800u + (uint32_t)pr.bitmap[ol * 80 + (s >> 1)] * (uint32_t)scale;
+            else if (s >= 176 && ol >= 3 && ol <= 8) v = 0x1800u + ((uint32_t)scale << ((((s - 176) >> 2) * 2 < pr.progress) ? 8 : 7));
+            w[i] = (v & 0xFFFFu) | (v << 16);
+        }
+    } else if (line < G::VSYNC && x0 + 8 <= G::HSYNC) w[0] = w[1] = w[2] = w[3] = SYNC2;
+    else if (line < G::VSYNC && (x0 >= G::BURST_START + G::BURST_W || (x0 >= G::HSYNC && x0 + 8 <= G::BURST_START))) w[0] = w[1] = w[2] = w[3] = BLACK2;
+    else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            w[i] = blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i) | (blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i + 1) << 16);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// four luma pixels + two chroma phase words -> eight samples (video.cpp:716-733, verbatim packed arithmetic)
+__device__ __forceinline__ uint4 blit_quad(uint32_t y4, uint32_t dither, uint32_t ca, uint32_t cb, uint32_t& lum)
+{
+    uint32_t p0 = (y4 + dither) & 0xFCFCFCFCu;
+    uint32_t p1 = ((p0 >> 1) + (p0 >> 9)) & 0xFCFCFCFCu;
+    p0 >>= 2; p1 >>= 2;
+    const uint32_t l = (((p0 & 0xFF) + lum) >> 1) & 0xFF;
+    lum = p0 >> 24;
+    return make_uint4(((l << 24) | ((p0 & 0xFF) << 8)) + ca, ((p1 << 24) | (p0 & 0xFF00)) + (ca << 8),
+                      ((p1 << 16) | (p0 >> 8)) + cb, (((p1 << 8) & 0xFF000000u) | (p0 >> 16)) + (cb << 8));
+}
+
+// grid: x = threads of one field / 256, y = stream. One thread = two adjacent 16-byte chunks (32 bytes out,
+// 8 luma pixels in: one 8-byte luma load, one 4-byte load per chroma plane). The pairing is phased so that
+// the blit span starts on a pair boundary (NTSC chunk 20: pairs (2j, 2j+1); PAL chunk 35: pairs (2j-1, 2j)).
+// A warp covers 16 consecutive pairs of TWO consecutive lines (lanes 0-15 the even line, lanes 16-31 the
+// odd one): in the tiled frame the two luma rows of a tile share 32-byte sectors and both lines read the same
+// chroma row, so every sector the warp fetches is used whole. Stores are 512 contiguous bytes per half-warp.
 template <bool kNtsc>
 __global__ void __launch_bounds__(256)
 ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter, const EfPresent pr)
 {
     using G = Geo<kNtsc>;
-    constexpr int CPL = G::W / 8;                                          // 16-byte chunks per line
-    constexpr int GROUPS = (CPL + 15) / 16;                                // warps per line pair
+    constexpr int CPL = G::W / 8;                                          // 16-byte chunks per line (even)
+    constexpr int PHASE = (G::BLIT / 8) & 1;                               // 0: pairs (2j, 2j+1); 1: pairs (2j-1, 2j), single chunks at both ends
+    constexpr int ITEMS = CPL / 2 + PHASE;                                 // work items per line
+    constexpr int GROUPS = (ITEMS + 15) / 16;                              // warps per line pair
     const EfDev& D = *Dp;
-    const uint32_t* tab = D.color_tab;                                     // 3 KB LUT: lives in L1 through the read-only path
+#ifndef EF_K2_LUT_SMEM
+    const uint32_t* tab = D.color_tab;                                     // 3 KB chroma LUT through L1 (measured faster than a shared-memory copy per CTA)
+#else
+    __shared__ uint32_t tab[768];
+    for (int i = threadIdx.x; i < 768; i += 256) tab[i] = D.color_tab[i];
+    __syncthreads();
+#endif
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     const uint32_t stream = blockIdx.y;
     const int pair = (int)(t / (GROUPS * 32)), r = (int)(t - (uint32_t)pair * (GROUPS * 32));
     const int lane = r & 31;
-    const int line = 2 * pair + (lane >> 4), k = (r >> 5) * 16 + (lane & 15);
-    if (pair >= G::LINES / 2 || k >= CPL) return;
-    const int x0 = k * 8;
-    uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)(line * CPL + k) * 8;
+    const int line = 2 * pair + (lane >> 4), j = (r >> 5) * 16 + (lane & 15);
+    if (pair >= G::LINES / 2 || j >= ITEMS) return;
+    const int c0 = 2 * j - PHASE;                                          // first chunk of the item; c0 == -1 / c0 + 1 == CPL: single chunk
+    uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)line * G::W;
 
     const int fl = line - G::TOP;                                          // frame line 0..191 on active lines
     const bool active = fl >= 0 && fl < EF_H && fb_sel != -2;              // -2: no frame presented yet (video.cpp:1140)
-    uint32_t w[4];
+    const int x0 = c0 * 8;
     if (active && x0 >= G::BLIT && x0 < G::BLIT + 2 * EF_W) {
         int fb = fb_sel >= 0 ? fb_sel : (int)((D.base_pics[stream] + D.n_pics[stream]) & 1u);
         // two-frame horizontal scroll (video.cpp:1146-1154): blit(f, dst, i, h, 352-h) then blit(f^1, dst + (352-h)*2, i, 0, h)
         int h = pr.hscroll;
         if (h < 0) { h += EF_W; fb ^= 1; }
-        const int qd = (x0 - G::BLIT) >> 3;                                // 4-pixel group of the destination, 0..87
-        const int split = (EF_W - h) >> 2;                                 // first group drawn by the second blit
-        const bool second = qd >= split;
+        const int gd = (x0 - G::BLIT) >> 4;                                // 8-pixel group of the destination, 0..43
+        const int split = (EF_W - h) >> 3;                                 // first group drawn by the second blit
+        const bool second = gd >= split;
         if (second) fb ^= 1;
-        const int q = second ? qd - split : qd + (h >> 2);                 // 4-pixel group of the source frame
-        const bool call_start = second ? q == 0 : qd == 0;                 // blit() starts its luma carry at 0
+        const int g = second ? gd - split : gd + (h >> 3);                 // 8-pixel group of the source frame
+        const bool call_start = second ? g == 0 : gd == 0;                 // blit() starts its luma carry at 0
         const uint8_t* f = D.frames + ef_frame_offset((int)stream, fb);
         const uint32_t dither = c_dither[(fl & 3) + ((frame_counter & 1) << 2)];
-        // tiled frame (ef_common.cuh): 4 luma pixels of group q sit in tile q>>2, the 2 chroma samples too
+        // tiled frame (ef_common.cuh): the 8 luma pixels of group g are half a tile row, the 4 chroma samples half a chroma tile row
         const int cy = fl >> 1;
-        const int ycol = (q >> 2) * EF_TILE + (q & 3) * 4, ccol = (q >> 2) * EF_TILE + 256 + (q & 3) * 2;
+        const int tcol = (g >> 1) * EF_TILE;
         const uint8_t* yrow = f + (fl >> 4) * EF_MBW_MAX * EF_TILE + (fl & 15) * 16;
-        const uint8_t* crow = f + (cy >> 3) * EF_MBW_MAX * EF_TILE + (cy & 7) * 8;       // get_cr(line>>1); get_cb is the next 64-byte plane
-        uint32_t u2 = *(const uint16_t*)(crow + ccol);
-        uint32_t v2 = *(const uint16_t*)(crow + ccol + 64);
+        const uint8_t* crow = f + (cy >> 3) * EF_MBW_MAX * EF_TILE + (cy & 7) * 8 + 256 + (g & 1) * 4;   // get_cr(line>>1); get_cb is the next 64-byte plane
+        uint32_t u4 = *(const uint32_t*)(crow + tcol);
+        uint32_t v4 = *(const uint32_t*)(crow + tcol + 64);
         int vt = 256;
         if (fl & 1) {                                                      // odd lines average with the next chroma row (video.cpp:704-716)
             const int n = cy + (fl == 191 ? 0 : 1);
-            const uint8_t* nrow = f + (n >> 3) * EF_MBW_MAX * EF_TILE + (n & 7) * 8;
-            const uint32_t ub = *(const uint16_t*)(nrow + ccol);
-            const uint32_t vb = *(const uint16_t*)(nrow + ccol + 64);
-            u2 = ((u2 >> 1) & 0x7F7Fu) + ((ub >> 1) & 0x7F7Fu);
-            v2 = ((v2 >> 1) & 0x7F7Fu) + ((vb >> 1) & 0x7F7Fu);
+            const uint8_t* nrow = f + (n >> 3) * EF_MBW_MAX * EF_TILE + (n & 7) * 8 + 256 + (g & 1) * 4;
+            u4 = ((u4 >> 1) & 0x7F7F7F7Fu) + ((*(const uint32_t*)(nrow + tcol) >> 1) & 0x7F7F7F7Fu);
+            v4 = ((v4 >> 1) & 0x7F7F7F7Fu) + ((*(const uint32_t*)(nrow + tcol + 64) >> 1) & 0x7F7F7F7Fu);
             vt = 512;
         }
-        const uint32_t ca = chroma_word(tab, u2, v2, vt), cb = chroma_word(tab, u2 >> 8, v2 >> 8, vt);
-        uint32_t lum = 0;                                                  // carry = pixel 3 of the previous group, 0 at the line start
-        if (!call_start) lum = ((((*(const uint32_t*)(yrow + ((q - 1) >> 2) * EF_TILE + ((q - 1) & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
-        uint32_t p0 = (*(const uint32_t*)(yrow + ycol) + dither) & 0xFCFCFCFCu;   // video.cpp:716-733, verbatim packed arithmetic
-        uint32_t p1 = ((p0 >> 1) + (p0 >> 9)) & 0xFCFCFCFCu;
-        p0 >>= 2; p1 >>= 2;
-        lum = (((p0 & 0xFF) + lum) >> 1) & 0xFF;
-        w[0] = ((lum << 24) | ((p0 & 0xFF) << 8)) + ca;
-        w[1] = ((p1 << 24) | (p0 & 0xFF00)) + (ca << 8);
-        w[2] = ((p1 << 16) | (p0 >> 8)) + cb;
-        w[3] = (((p1 << 8) & 0xFF000000u) | (p0 >> 16)) + (cb << 8);
-    } else {
-        // blank and vsync lines, and the part of an active line outside the blit span (which still
-        // shows what blanking() last left in the ping-pong buffer: sync, burst, BLACK). Most chunks
-        // lie wholly inside one constant region: decide per chunk, fall back to per-sample only at
-        // the burst and on the vsync lines.
-        const uint32_t SYNC2 = 0x00000000u, BLACK2 = 0x18001800u;
-        const int ol = line - (G::TOP + EF_H + 2);                         // overlay line 0..15 (video.cpp:1183-1189)
-        if (pr.blend != 0 && ol >= 0 && ol < 16 && x0 >= G::BLIT + 16 && x0 < G::BLIT + 16 + 160 + 16 + 480) {
-            // composite(), video.cpp:845-887: 80 bitmap bytes -> 160 samples, then (lines 3..8) a 480-sample progress bar
-            int scale = 255 / 4;
-            if (pr.blend != -1 && pr.blend < 32) scale = (scale * pr.blend) >> 5;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int s = x0 + 2 * i - (G::BLIT + 16);                 // both samples of a word share the source byte / bar step
-                uint32_t v = 0x1800u;
-                if (s < 160) v = 0x1800u + (uint32_t)pr.bitmap[ol * 80 + (s >> 1)] * (uint32_t)scale;
-                else if (s >= 176 && ol >= 3 && ol <= 8) v = 0x1800u + ((uint32_t)scale << ((((s - 176) >> 2) * 2 < pr.progress) ? 8 : 7));
-                w[i] = (v & 0xFFFFu) | (v << 16);
-            }
-        } else if (line < G::VSYNC && x0 + 8 <= G::HSYNC) w[0] = w[1] = w[2] = w[3] = SYNC2;
-        else if (line < G::VSYNC && (x0 >= G::BURST_START + G::BURST_W || (x0 >= G::HSYNC && x0 + 8 <= G::BURST_START))) w[0] = w[1] = w[2] = w[3] = BLACK2;
-        else {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                w[i] = blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i) | (blank_sample<kNtsc>(D.pal_burst, line, x0 + 2 * i + 1) << 16);
+        const uint2 y8 = *(const uint2*)(yrow + tcol + (g & 1) * 8);
+        uint32_t lum = 0;                                                  // carry = last pixel of the previous group, 0 at the start of a blit() call
+        if (!call_start) {
+            const int q = 2 * g - 1;                                       // previous 4-pixel group
+            lum = ((((*(const uint32_t*)(yrow + (q >> 2) * EF_TILE + (q & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
         }
+        const uint4 o0 = blit_quad(y8.x, dither, chroma_word(tab, u4, v4, vt), chroma_word(tab, u4 >> 8, v4 >> 8, vt), lum);
+        const uint4 o1 = blit_quad(y8.y, dither, chroma_word(tab, u4 >> 16, v4 >> 16, vt), chroma_word(tab, u4 >> 24, v4 >> 24, vt), lum);
+        __stcs((uint4*)(out + x0), o0);                                    // streaming stores: the field is not re-read by this kernel
+        __stcs((uint4*)(out + x0 + 8), o1);
+    } else {
+        if (c0 >= 0) __stcs((uint4*)(out + x0), blank_chunk<kNtsc>(D, pr, line, x0));
+        if (c0 + 1 < CPL) __stcs((uint4*)(out + x0 + 8), blank_chunk<kNtsc>(D, pr, line, x0 + 8));
     }
-    __stcs((uint4*)out, make_uint4(w[0], w[1], w[2], w[3]));               // streaming store: the field is not re-read by this kernel
 }
 
 // single blit() call into a device buffer (line-blit entry point; used by ef_blit): one thread per 4 luma pixels
@@ -199,7 +227,8 @@ __global__ void ef_blit_kernel(const EfDev* __restrict__ Dp, int stream, int fb,
 
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream)
 {
-    const unsigned groups = ((unsigned)(g.line_width >> 3) + 15) / 16;
+    const unsigned items = (unsigned)(g.line_width >> 4) + (((unsigned)g.blit_start >> 3) & 1u);   // 32-byte work items per line (see the kernel)
+    const unsigned groups = (items + 15) / 16;
     const unsigned threads = groups * 32 * (unsigned)(g.line_count / 2);   // both standards have an even line count
     const dim3 grid((threads + 255) / 256, (unsigned)n_streams);
     if (g.ntsc) ef_composite_kernel<true><<<grid, 256, 0, stream>>>(dev, fb, frame_counter, pr);
