@@ -34,13 +34,18 @@ namespace {
 
 constexpr int kWarpsPerCta = EF_K1_WARPS;
 constexpr int kListEntries = EF_K1_LIST;        // per-lane coefficient list capacity in shared memory
-constexpr int kListBytes = 32 * kListEntries * 4;
+#ifdef EF_K1_HALF
+constexpr int kLanes = 16;                      // tuning experiment: 16 slices per warp
+#else
+constexpr int kLanes = 32;                      // slices (parser lanes) per warp
+#endif
+constexpr int kListBytes = kLanes * kListEntries * 4;
 constexpr int kHdrStride = 44;                  // bytes per lane header; 11 words (odd) -> conflict-free
 constexpr int kHdrDc = 0;                       // int32 [6] intra DC (pixel scale)
 constexpr int kHdrInfo = 24;                    // bit0 valid, 1 intra, 2-7 coded blocks, 8-13 n==1 mask, 14-19 abort mask (bit b = block b), 20-24 mb_x, 25-28 mb_y
 constexpr int kHdrCnt = 28;                     // list entries | skip_before << 16
 constexpr int kHdrMv = 32;                      // (int16 h) | (int16 v) << 16, half-pel units
-constexpr int kHdrBytes = 32 * kHdrStride;
+constexpr int kHdrBytes = kLanes * kHdrStride;
 constexpr int kDenseStride = 72;                // words per block in the dense scratch: 64 + 8 pad -> the 4 luma blocks hit distinct banks
 constexpr int kDenseBytes = 6 * kDenseStride * 4;   // int32 [6][72] prescaled coefficients, raster order; also the IDCT transpose buffer
 constexpr int kStageBytes = 4 * EF_TILE;        // motion-compensation staging: up to 2 x 2 reference tiles per macroblock
@@ -411,8 +416,8 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* wbase = smem + kTableBytes + (size_t)warp * kWarpBytes;
-    uint32_t* list = (uint32_t*)wbase + lane * kListEntries;
-    uint8_t* hdr = wbase + kListBytes + lane * kHdrStride;
+    uint32_t* list = (uint32_t*)wbase + (lane % kLanes) * kListEntries;
+    uint8_t* hdr = wbase + kListBytes + (lane % kLanes) * kHdrStride;
     int* dense = (int*)(wbase + kListBytes + kHdrBytes);
     uint8_t* stage = wbase + kListBytes + kHdrBytes + kDenseBytes;
     uint64_t* bar = (uint64_t*)(stage + kStageBytes);
@@ -442,8 +447,15 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
     // the SMs - with fewer slices than lanes (4,096 pictures x 12 slices vs 71 K lanes) every SM then runs
     // the same number of full warps instead of whichever warps reach the cursor first. Later rounds (lanes
     // whose slice ended) pull from the global cursor, which counts from the end of the first round.
+#ifdef EF_K1_HALF
+    const uint32_t first_round = gridDim.x * (uint32_t)kWarpsPerCta * 16u;
+#else
     const uint32_t first_round = gridDim.x * (uint32_t)kWarpsPerCta * 32u;
+#endif
     bool first_fill = true;
+#ifdef EF_K1_HALF   // tuning experiment: only 16 slices per warp (twice the warps for the same batch)
+    if (lane >= 16) exhausted = true;
+#endif
 
     for (;;) {
         // ---- refill idle lanes with new slices -------------------------------------------------
@@ -451,7 +463,11 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
         if (need) {
             uint32_t base;
             if (first_fill) {
+#ifdef EF_K1_HALF
+                base = ((uint32_t)warp * gridDim.x + blockIdx.x) * 16u;
+#else
                 base = ((uint32_t)warp * gridDim.x + blockIdx.x) * 32u;
+#endif
                 first_fill = false;
             } else {
                 base = 0;
