@@ -22,9 +22,10 @@ __global__ void ef_fill_kernel(EfDev* Dp);
 __global__ void ef_ts_len_kernel(const uint8_t* ts, uint64_t n_packets, uint32_t* out_len);
 __global__ void ef_ts_copy_kernel(const uint8_t* ts, uint64_t n_packets, const uint64_t* out_off, uint8_t* es);
 __global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint64_t* off, const uint64_t* ts_off, int n_streams, uint64_t* es_off, uint8_t* es);
-size_t ef_decode_smem_bytes();
+size_t ef_recon_smem_bytes();
 cudaError_t ef_decode_configure();
-cudaError_t ef_launch_decode(const EfDev* dev, int pic, int ctas, cudaStream_t stream);
+cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream);
+cudaError_t ef_launch_recon(const EfDev* dev, int pic, int pic_rel, int sm_count, cudaStream_t stream);
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream);
 cudaError_t ef_launch_blit(const EfDev* dev, int stream_index, int fb, int line, int x, int width, int frame_counter, uint16_t* dst, cudaStream_t stream);
 
@@ -193,9 +194,9 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     c->sm_count = prop.multiProcessorCount;
-    if ((size_t)prop.sharedMemPerBlockOptin < ef_decode_smem_bytes()) {
+    if ((size_t)prop.sharedMemPerBlockOptin < ef_recon_smem_bytes()) {
         delete c;
-        return fail(EF_ECUDA, "device offers %zu B shared memory per CTA, kernel needs %zu", (size_t)prop.sharedMemPerBlockOptin, ef_decode_smem_bytes());
+        return fail(EF_ECUDA, "device offers %zu B shared memory per CTA, kernel needs %zu", (size_t)prop.sharedMemPerBlockOptin, ef_recon_smem_bytes());
     }
     CK(ef_decode_configure());
     CK(ef_index_upload_constants());
@@ -233,7 +234,15 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     A(h.work, h.work_capacity);
     A(h.info, 8);
     EfTables* dt; A(dt, 1);
-    A(h.k1_overflow, (size_t)c->sm_count * EF_K1_WARPS * 32 * (384 - EF_K1_LIST));
+    A(h.parse_cursor, 4);
+    {   // macroblock records: as many picture indices per K1a launch as fit in 2 GiB
+        const size_t per_pic = (size_t)n * EF_MBW_MAX * EF_MBH_MAX * (sizeof(EfMbRec) + 4);
+        size_t k = ((size_t)2 << 30) / per_pic;
+        h.rec_pics = (int)(k < 1 ? 1 : k > (size_t)h.max_pictures ? (size_t)h.max_pictures : k);
+        const size_t slots = (size_t)h.rec_pics * n * EF_MBW_MAX * EF_MBH_MAX;
+        A(h.mb_info, slots); A(h.mb_rec, slots);
+        A(h.coef, 3 * (cfg->es_capacity + 1024) + 1024);
+    }
     A(c->d_color_tab, 768); A(c->d_pal_burst, 128); A(c->d_default_intra, 64); A(c->d_overlay, 1280);
     c->present.bitmap = c->d_overlay;
     if (cfg->fields) { h.field_stride = EF_PAL_FIELD_SAMPLES; A(h.fields, (size_t)n * h.field_stride); }
@@ -411,23 +420,35 @@ int ef_stream_info(ef_ctx* c, int stream_index, int* n_pictures, int* base_pictu
     return EF_OK;
 }
 
+// K1a over picture indices [p0, p0 + k), then K1b once per picture index
+static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st)
+{
+    const size_t slots = (size_t)k * c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX;
+    CK(cudaMemsetAsync(c->h.mb_info, 0, slots * 4, st));
+    CK(cudaMemsetAsync(c->h.parse_cursor, 0, 4, st));
+    CK(ef_launch_parse(c->d, p0, k, c->sm_count, st));
+    for (int i = 0; i < k; i++) CK(ef_launch_recon(c->d, p0 + i, i, c->sm_count, st));
+    CK(cudaEventRecord(c->ev_buf_free[c->active], st));     // the front ES buffer is in use until here
+    c->launches += 1 + (uint64_t)k;
+    return EF_OK;
+}
+
 int ef_decode_picture(ef_ctx* c, int pic, void* stream)
 {
     if (!c) return fail(EF_EINVAL, "null context");
     if (!c->indexed) return fail(EF_ESTATE, "ef_decode_picture before ef_index");
     if (pic < 0 || pic >= c->cfg.max_pictures) return fail(EF_EINVAL, "picture index %d out of range", pic);
-    CK(ef_launch_decode(c->d, pic, c->sm_count, (cudaStream_t)stream));
-    CK(cudaEventRecord(c->ev_buf_free[c->active], (cudaStream_t)stream));     // the front ES buffer is in use until here
-    c->launches++;
-    return EF_OK;
+    return decode_range(c, pic, 1, (cudaStream_t)stream);
 }
 
 int ef_decode_all(ef_ctx* c, int n_pictures, void* stream)
 {
     if (!c) return fail(EF_EINVAL, "null context");
+    if (!c->indexed) return fail(EF_ESTATE, "ef_decode_all before ef_index");
     if (n_pictures < 0 || n_pictures > c->cfg.max_pictures) return fail(EF_EINVAL, "n_pictures %d out of range", n_pictures);
-    for (int p = 0; p < n_pictures; p++) {
-        int rc = ef_decode_picture(c, p, stream);
+    for (int p = 0; p < n_pictures; p += c->h.rec_pics) {
+        const int k = n_pictures - p < c->h.rec_pics ? n_pictures - p : c->h.rec_pics;
+        int rc = decode_range(c, p, k, (cudaStream_t)stream);
         if (rc != EF_OK) return rc;
     }
     return EF_OK;

@@ -16,7 +16,10 @@
 //                                               entry 0 = state carried in from the previous submit
 //   pics          [n_streams][max_pictures]     per picture: type, full_pel, r_size, seq index, first slice
 //   slices        [n_streams][max_slices]       per slice: byte offset after its start code, slice code
-//   work          [total slices]                flat per-picture slice work lists (K1's unit of work)
+//   work          [total slices]                flat per-picture slice work lists (K1a's unit of work)
+//   mb_info/mb_rec[rec_pics][n_streams][264]    macroblock records K1a -> K1b, slot = macroblock address
+//   coef          [3 x es bytes] u32            coefficient lists K1a -> K1b; the list of a slice starts at
+//                                               entry 3 x (its byte offset in `es`)
 //   fields        [n_streams][field samples]    composite output of K2 (u16)
 #pragma once
 #include <cuda_runtime.h>
@@ -29,11 +32,17 @@
 #define EF_MBW_MAX 22
 #define EF_MBH_MAX 12
 #define EF_TILE 384          // bytes per macroblock tile: 256 Y + 64 + 64 chroma
-#ifndef EF_K1_WARPS
-#define EF_K1_WARPS 15       // warps per K1 CTA (one CTA per SM; shared-memory bound)
+#ifndef EF_K1A_THREADS
+#define EF_K1A_THREADS 256   // K1a (parse): threads per CTA, CTAs per SM (register bound)
 #endif
-#ifndef EF_K1_LIST
-#define EF_K1_LIST 80        // per-lane coefficient list entries kept in shared memory (rest spills to HBM)
+#ifndef EF_K1A_CTAS
+#define EF_K1A_CTAS 4
+#endif
+#ifndef EF_K1B_WARPS
+#define EF_K1B_WARPS 8       // K1b (reconstruct): warps per CTA, CTAs per SM
+#endif
+#ifndef EF_K1B_CTAS
+#define EF_K1B_CTAS 4
 #endif
 
 // ---- decode tables (built on the host by ef_tables.cpp from ISO 11172-2 Annex B) -------------
@@ -83,7 +92,15 @@ struct __align__(16) EfWork {   // one slice of one stream for one picture index
     uint32_t stream;
     uint32_t es_off;        // byte offset (relative to the stream start) of the first byte after the start code
     uint32_t info;          // bits0-7 slice code, 8-10 picture type, 11 full_pel, 12-14 r_size, 16-31 seq index
-    uint32_t pad;
+    uint32_t pic;           // picture index inside the submit
+};
+
+struct __align__(16) EfMbRec {  // one parsed macroblock (K1a -> K1b); its info word lives in EfDev::mb_info
+    uint32_t cnt;           // coefficient entries | skipped macroblocks before this one << 16
+    uint32_t mv;            // (int16 h) | (int16 v) << 16, half-pel units
+    uint32_t list_lo, list_hi;   // index of the first entry in EfDev::coef
+    int32_t dc[6];          // intra DC, pixel scale
+    uint32_t pad[2];
 };
 
 struct EfGeometry {          // video.cpp:572-630, values probe-verified in tests/golden/composite_pins.json
@@ -113,11 +130,15 @@ struct EfDev {               // device-visible context (lives in device memory)
     uint32_t* pic_pref;      // [max_pictures][n_streams] exclusive prefix of n_slices over streams
     uint32_t* pic_total;     // [max_pictures] slices of that picture index over all streams
     uint32_t* pic_base;      // [max_pictures] start of that picture's range in `work`
-    uint32_t* cursor;        // [max_pictures] work-stealing cursor of K1
+    uint32_t* cursor;        // [max_pictures] (kept for the index kernels)
+    uint32_t* parse_cursor;  // work-stealing cursor of K1a, zeroed before every launch
     EfWork* work;            // flat, grouped by picture index
     uint32_t* info;          // [8]: 0 max pictures, 1 total pictures, 2 total slices, 3 error flags
     const EfTables* tables;
-    uint32_t* k1_overflow;   // [K1 lanes][384 - EF_K1_LIST] spill area of the per-lane coefficient lists
+    uint32_t* mb_info;       // [rec_pics][n_streams][264] info word per macroblock slot (0 = nothing to rebuild), zeroed before every K1a launch
+    EfMbRec* mb_rec;         // [rec_pics][n_streams][264]
+    uint32_t* coef;          // [3 * (es_capacity + 1024)] coefficient entries
+    int rec_pics;            // picture indices one K1a launch can cover
     uint16_t* fields;        // [n_streams][field_stride]
     const uint32_t* color_tab;   // [768]
     const int16_t* pal_burst;    // [2][64]

@@ -1,29 +1,33 @@
-// espflix_b200/csrc/ef_decode.cu — K1, the fused macroblock kernel (one launch per picture index
-// over the whole batch of streams).
+// espflix_b200/csrc/ef_decode.cu — K1, the macroblock decoder, as a pair of kernels.
 //
 // Replaces, for every stream at once, MpegDecoder::slice() and everything under it
 // (player.cpp:733-1316): macroblock-header VLC, motion vectors, block() coefficient VLC +
 // dequantisation, idct(), mocomp()/predict_zero(), copy_block/add_block with the [0,248] clamp.
 //
-// Mapping (B200-first, not a translation of the reference's single scalar loop):
-//   * unit of work = one slice of one stream (EfWork). VLC parsing is serial inside a slice, so the
-//     parallelism is streams x slices: every LANE of a warp parses a different slice, one
-//     macroblock per iteration. The macroblock header is parsed by all lanes together; the
-//     coefficients are then decoded by a FLAT per-lane state machine (one symbol per step, lanes
-//     move through their blocks independently): CLZ-indexed shared-memory table -> (run, level,
-//     length) in one load, dequantised on the spot (quirk Q2 included) and appended as a 32-bit
-//     (block, scan position, value) entry to the lane's list in shared memory (96 entries; the rare
-//     longer macroblock spills to a per-lane HBM area).
-//   * then the whole WARP reconstructs the 32 macroblocks one after another: scatter the list into
-//     a dense 6x64 scratch (values already de-zigzagged and AAN-prescaled by the parser), the
-//     reference's integer AAN IDCT in place with one lane per block column, then per block row
-//     (4 luma blocks = 32 lanes), half-pel motion compensation and the clamped add with one lane
-//     per 8-pixel row segment.
+// The reference interleaves bitstream parsing and pixel reconstruction macroblock by macroblock.
+// The two halves have opposite shapes on a GPU, so they are separate kernels here:
+//
+//   K1a ef_parse_kernel   bitstream -> macroblock records. VLC parsing is serial inside a slice and
+//       needs NO pixel data, so every slice of EVERY picture of the submit is independent: one launch
+//       covers pictures x streams x slices (589,824 slices for the BASELINE batch), one slice per
+//       LANE, lanes pulling new slices from a global cursor as they finish. Per macroblock a lane
+//       emits (i) a 48-byte record (type, coded-block pattern, motion vector, intra DCs, skip run,
+//       list position) in the slot of its macroblock ADDRESS and (ii) its coefficients as 32-bit
+//       entries (block, raster position, dequantised + AAN-prescaled value), appended to the slice's
+//       list in HBM. A VLC symbol is one CLZ + one shared-memory table load; dequantisation
+//       (quirk Q2 included) happens on the spot. The list of a slice starts at entry 3 x (byte offset
+//       of the slice in the ES blob): every coefficient costs at least 3 bits of bitstream, so lists
+//       can never run into each other and no allocation or prefix sum is needed.
+//   K1b ef_recon_kernel   records -> pixels, one launch per picture index (P pictures read the
+//       previous picture of their stream). One WARP per macroblock record, all 1,081,344 of a
+//       BASELINE picture batch independent: scatter the list into a dense 6x64 scratch, the
+//       reference's integer AAN IDCT in place (one lane per block column, then per block row), half-pel
+//       motion compensation from reference tiles staged by TMA bulk copies, the clamped add, 8-byte
+//       stores. Records of the next macroblock are prefetched while the current one is rebuilt.
+//
 //   * frame stores are MACROBLOCK-TILED in HBM (ef_common.cuh): a macroblock is 384 contiguous
 //     bytes, so the warp's stores are two full 128-byte lines + one more for chroma, no partial
 //     sectors; motion-compensated reads touch <= 4 tiles.
-//   * lanes that finish a slice pull the next one from a global cursor, so lane occupancy stays
-//     high until the picture's work list is empty (persistent CTAs, one per SM, 14 warps).
 // Bit-exactness notes: Q1 clamp [0,248]; Q2 oddification maps 0 -> +1; Q3 chroma
 // vector = floor(luma position / 2); Q4 matrices indexed in raster order (done at index time);
 // Q5 single-coefficient blocks bypass the IDCT with floor; Q6 first macroblock of a slice lands in
@@ -32,24 +36,17 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = EF_K1_WARPS;
-constexpr int kListEntries = EF_K1_LIST;        // per-lane coefficient list capacity in shared memory
-#ifdef EF_K1_HALF
-constexpr int kLanes = 16;                      // tuning experiment: 16 slices per warp
-#else
-constexpr int kLanes = 32;                      // slices (parser lanes) per warp
-#endif
-constexpr int kListBytes = kLanes * kListEntries * 4;
-constexpr int kHdrStride = 44;                  // bytes per lane header; 11 words (odd) -> conflict-free
-constexpr int kHdrDc = 0;                       // int32 [6] intra DC (pixel scale)
-constexpr int kHdrInfo = 24;                    // bit0 valid, 1 intra, 2-7 coded blocks, 8-13 n==1 mask, 14-19 abort mask (bit b = block b), 20-24 mb_x, 25-28 mb_y
-constexpr int kHdrCnt = 28;                     // list entries | skip_before << 16
-constexpr int kHdrMv = 32;                      // (int16 h) | (int16 v) << 16, half-pel units
-constexpr int kHdrBytes = kLanes * kHdrStride;
+constexpr int kParseThreads = EF_K1A_THREADS;   // per CTA
+constexpr int kParseCtasPerSm = EF_K1A_CTAS;
+constexpr int kReconWarps = EF_K1B_WARPS;       // per CTA
+constexpr int kReconCtasPerSm = EF_K1B_CTAS;
+
+// macroblock info word (EfDev::mb_info): bit0 valid, 1 intra, 2-7 coded blocks, 8-13 n==1 mask,
+// 14-19 abort mask (bit b = block b), 20-24 mb_width of the stream
 constexpr int kDenseStride = 72;                // words per block in the dense scratch: 64 + 8 pad -> the 4 luma blocks hit distinct banks
-constexpr int kDenseBytes = 6 * kDenseStride * 4;   // int32 [6][72] prescaled coefficients, raster order; also the IDCT transpose buffer
+constexpr int kDenseBytes = 8 * kDenseStride * 4;   // int32 [6][72] prescaled coefficients, raster order, also the IDCT transpose buffer; + 2 dump blocks for malformed entries
 constexpr int kStageBytes = 4 * EF_TILE;        // motion-compensation staging: up to 2 x 2 reference tiles per macroblock
-constexpr int kWarpBytes = kListBytes + kHdrBytes + kDenseBytes + kStageBytes + 16;   // + the warp's mbarrier
+constexpr int kWarpBytes = kDenseBytes + kStageBytes + 16;   // + the warp's mbarrier
 
 struct SharedTables {                           // same layout as the head of EfTables
     uint16_t dct[26 * 32];
@@ -106,8 +103,8 @@ struct BitReader {
 // per-lane slice parser state
 struct SliceState {
     BitReader br;
-    uint8_t* cur;
-    const uint8_t* ref;
+    uint32_t* wptr;          // next free entry of this slice's coefficient list in HBM
+    uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture
     const uint8_t* qtab;     // scan-order quantiser tables [intra 64 | non-intra 64]: the shared-memory defaults or the stream's own in HBM
     int mbw, mbh;
     int mb_x, mb_y;          // last macroblock handled
@@ -303,9 +300,10 @@ __device__ __forceinline__ void pred_finish(const PredWords& w, int x, int xh, i
 
 // ---------------------------------------------------------------------------------------------
 // macroblock header of this lane's slice (player.cpp:1266-1307). Returns false when the slice
-// ended. On success: hdr is filled, `cbp` = blocks to parse (bit b = block b), `intra` set.
+// ended. On success: `cbp` = blocks to parse (bit b = block b), `intra`, the skip run before this
+// macroblock and its motion vector in half-pel units ((int16 h) | (int16 v) << 16).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool parse_header(SliceState& s, uint8_t* hdr, const SharedTables& T, int& cbp_out, int& intra_out)
+__device__ __forceinline__ bool parse_header(SliceState& s, const SharedTables& T, int& cbp_out, int& intra_out, uint32_t& skip_out, uint32_t& mv_out)
 {
     BitReader& br = s.br;
     uint32_t bits = br.peek();
@@ -367,11 +365,10 @@ __device__ __forceinline__ bool parse_header(SliceState& s, uint8_t* hdr, const 
         cbp = (int)(e >> 4);
         br.skip(e & 15);
     }
-    cbp = (int)(__brev((unsigned)cbp) >> 26);       // bit b = block b (the VLC value has block 0 in bit 5)
-    *(uint32_t*)(hdr + kHdrInfo) = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp << 2) | ((uint32_t)s.mb_x << 20) | ((uint32_t)s.mb_y << 25);
-    *(uint32_t*)(hdr + kHdrCnt) = (uint32_t)skip_before << 16;
-    *(uint32_t*)(hdr + kHdrMv) = ((uint32_t)mvh & 0xFFFFu) | ((uint32_t)mvv << 16);
-    cbp_out = cbp; intra_out = intra;
+    cbp_out = (int)(__brev((unsigned)cbp) >> 26);   // bit b = block b (the VLC value has block 0 in bit 5)
+    intra_out = intra;
+    skip_out = (uint32_t)skip_before;
+    mv_out = ((uint32_t)mvh & 0xFFFFu) | ((uint32_t)mvv << 16);
     return true;
 }
 
@@ -403,10 +400,13 @@ __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
 
 }  // namespace
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1)
-ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
+// =================================================================================================
+// K1a: bitstream -> macroblock records, every slice of pictures [pic0, pic0 + n_pics) in one launch
+// =================================================================================================
+__global__ void __launch_bounds__(kParseThreads, kParseCtasPerSm)
+ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(16) uint8_t smem[kTableBytes];
     SharedTables& T = *(SharedTables*)smem;
     const EfDev& D = *Dp;
     {   // stage the tables (the first sizeof(SharedTables) bytes of EfTables have the same layout)
@@ -414,48 +414,21 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
         uint32_t* dst = (uint32_t*)smem;
         for (int i = threadIdx.x; i < (int)(sizeof(SharedTables) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t* wbase = smem + kTableBytes + (size_t)warp * kWarpBytes;
-    uint32_t* list = (uint32_t*)wbase + (lane % kLanes) * kListEntries;
-    uint8_t* hdr = wbase + kListBytes + (lane % kLanes) * kHdrStride;
-    int* dense = (int*)(wbase + kListBytes + kHdrBytes);
-    uint8_t* stage = wbase + kListBytes + kHdrBytes + kDenseBytes;
-    uint64_t* bar = (uint64_t*)(stage + kStageBytes);
-    const uint32_t sstage = smem_u32(stage), sbar = smem_u32(bar);
-    uint32_t bar_phase = 0;
-    if (lane == 0) mbar_init(bar, 1);
-    uint32_t* ovf = D.k1_overflow + ((size_t)(blockIdx.x * kWarpsPerCta + warp) * 32 + lane) * (384 - kListEntries);
-    for (int i = lane; i < kDenseBytes / 4; i += 32) ((uint32_t*)dense)[i] = 0;
     __syncthreads();
+    const int lane = threadIdx.x & 31;
 
-    const uint32_t total = D.pic_total[pic];
-    const EfWork* work = D.work + D.pic_base[pic];
-    uint32_t* cursor = D.cursor + pic;
-
-    // per-lane constants of the reconstruction mapping
-    const int col = lane & 7;                       // column owned in the IDCT column pass
-    const int cblk = lane >> 3;                     // block (0..3) owned in the column pass
-    const int prow = lane >> 1, phalf = lane & 1;   // luma pixel row / 8-pixel half owned for prediction + store
-    const int rblk = (prow >> 3) * 2 + phalf;       // block that those pixels belong to
-    const int rrow = prow & 7;                      // row of that block
-    const int crow = lane & 7, cplane = (lane >> 3) & 1;   // chroma row / plane owned by lanes 0..15
+    // the work lists of consecutive picture indices are contiguous (ef_prefix_kernel)
+    uint32_t total = 0;
+    for (int p = pic0; p < pic0 + n_pics; p++) total += D.pic_total[p];
+    const EfWork* work = D.work + D.pic_base[pic0];
+    const uint32_t n_slots = (uint32_t)D.n_streams * (EF_MBW_MAX * EF_MBH_MAX);
 
     SliceState s;
-    s.first = 0; s.cur = nullptr; s.ref = nullptr; s.qtab = T.qdef; s.mbw = 0;
+    s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qtab = T.qdef; s.mbw = 0;
     bool active = false, exhausted = false;
-    // First round: slices are dealt out statically, 32 consecutive ones per warp, warps interleaved across
-    // the SMs - with fewer slices than lanes (4,096 pictures x 12 slices vs 71 K lanes) every SM then runs
-    // the same number of full warps instead of whichever warps reach the cursor first. Later rounds (lanes
-    // whose slice ended) pull from the global cursor, which counts from the end of the first round.
-#ifdef EF_K1_HALF
-    const uint32_t first_round = gridDim.x * (uint32_t)kWarpsPerCta * 16u;
-#else
-    const uint32_t first_round = gridDim.x * (uint32_t)kWarpsPerCta * 32u;
-#endif
+    // first round: thread t takes slice t; afterwards lanes whose slice ended pull from the cursor
+    const uint32_t first_round = gridDim.x * blockDim.x;
     bool first_fill = true;
-#ifdef EF_K1_HALF   // tuning experiment: only 16 slices per warp (twice the warps for the same batch)
-    if (lane >= 16) exhausted = true;
-#endif
 
     for (;;) {
         // ---- refill idle lanes with new slices -------------------------------------------------
@@ -463,16 +436,12 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
         if (need) {
             uint32_t base;
             if (first_fill) {
-#ifdef EF_K1_HALF
-                base = ((uint32_t)warp * gridDim.x + blockIdx.x) * 16u;
-#else
-                base = ((uint32_t)warp * gridDim.x + blockIdx.x) * 32u;
-#endif
+                base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
                 first_fill = false;
             } else {
                 base = 0;
                 int leader = __ffs(need) - 1;
-                if (lane == leader) base = first_round + atomicAdd(cursor, (uint32_t)__popc(need));
+                if (lane == leader) base = first_round + atomicAdd(D.parse_cursor, (uint32_t)__popc(need));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
             }
             if (!active && !exhausted) {
@@ -486,10 +455,10 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                     s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
                     s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
                     s.qtab = seq->custom ? (const uint8_t*)seq->q_scan : (const uint8_t*)T.qdef;
-                    const uint32_t fb = (D.base_pics[w.stream] + (uint32_t)pic + 1u) & 1u;     // flush_picture(), player.cpp:692
-                    s.cur = D.frames + ef_frame_offset((int)w.stream, (int)fb);
-                    s.ref = D.frames + ef_frame_offset((int)w.stream, (int)(fb ^ 1u));
-                    s.br.init(D.es, D.es_off[w.stream] + w.es_off);
+                    const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
+                    s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
+                    s.wptr = D.coef + 3 * byte_off;          // >= 3 bits of bitstream per coefficient: lists cannot collide
+                    s.br.init(D.es, byte_off);
                     s.mb_y = code - 2; s.mb_x = s.mbw - 1;   // slice(), player.cpp:1255: the first increment lands on column 0 of row code-1
                     s.first = 1;
                     s.dc_y = s.dc_cr = s.dc_cb = 128; s.mv_h = s.mv_v = 0;
@@ -503,17 +472,21 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
         }
         if (__all_sync(0xFFFFFFFFu, !active)) break;
 
-        // ---- phase 1a: every lane parses the header of the next macroblock of its slice ---------
+        // ---- every lane parses the header of the next macroblock of its slice -------------------
         bool have = false;
         int cbp_rem = 0, intra = 0;
+        uint32_t skipw = 0, mvw = 0;
         if (active) {
-            have = parse_header(s, hdr, T, cbp_rem, intra);
+            have = parse_header(s, T, cbp_rem, intra, skipw, mvw);
             if (!have) active = false;
         }
+        const int cbp_all = cbp_rem;
+        const uint32_t slot = s.slot_base + (uint32_t)(s.mb_y * EF_MBW_MAX + s.mb_x);
+        EfMbRec* rec = D.mb_rec + slot;
+        uint32_t* const list0 = s.wptr;
 
-        // ---- phase 1b: flat coefficient state machine, one VLC symbol per lane per step ----------
-        int cnt = 0, n1mask = 0, abortmask = 0, blk = 0, n = 0;
-        uint32_t* wptr = list;
+        // ---- flat coefficient state machine, one VLC symbol per lane per step ---------------------
+        int n1mask = 0, abortmask = 0, blk = 0, n = 0;
         bool busy = have && cbp_rem != 0, start = true;
         const uint8_t* qrow = s.qtab + (intra ? 0 : 64);
         while (__any_sync(0xFFFFFFFFu, busy)) {
@@ -523,7 +496,7 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                     blk = __ffs(cbp_rem) - 1;
                     cbp_rem &= cbp_rem - 1;
                     n = 0;
-                    if (intra) { ((int*)(hdr + kHdrDc))[blk] = parse_dc(s, blk); n = 1; }
+                    if (intra) { rec->dc[blk] = parse_dc(s, blk); n = 1; }
                     start = false;
                 }
                 const uint32_t bits = br.peek();
@@ -557,9 +530,7 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
                         else {
                             const int v = dequant(level, intra, s.qscale * (int)qrow[n]);
                             const uint32_t zp = T.zp[n];                                   // zz = zig_zag[n]; b[zz] = v * scale_dct_q[zz] (player.cpp:1108, 1121)
-                            const uint32_t ent = ((uint32_t)(v * (int)(zp >> 8)) & 0x3FFFFu) | ((zp & 63u) << 18) | ((uint32_t)blk << 24);
-                            *wptr++ = ent;
-                            if (++cnt == kListEntries) wptr = ovf;                 // spill the rest of a very long macroblock to HBM
+                            *s.wptr++ = ((uint32_t)(v * (int)(zp >> 8)) & 0x3FFFFu) | ((zp & 63u) << 18) | ((uint32_t)blk << 24);
                             n++;
                         }
                     }
@@ -568,191 +539,255 @@ ef_decode_kernel(const EfDev* __restrict__ Dp, int pic)
             }
         }
         if (have) {
-            *(uint32_t*)(hdr + kHdrInfo) |= ((uint32_t)n1mask << 8) | ((uint32_t)abortmask << 14);
-            *(uint32_t*)(hdr + kHdrCnt) |= (uint32_t)cnt;
-        }
-        unsigned todo = __ballot_sync(0xFFFFFFFFu, have);
-        __syncwarp();
-
-        // ---- phase 2: the warp reconstructs those macroblocks one by one -----------------------
-        while (todo) {
-            const int r = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint8_t* H = wbase + kListBytes + r * kHdrStride;
-            const uint32_t info = *(const uint32_t*)(H + kHdrInfo);
-            const uint32_t cntw = *(const uint32_t*)(H + kHdrCnt);
-            const uint32_t mvw = *(const uint32_t*)(H + kHdrMv);
-            uint8_t* cur = (uint8_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)s.cur, r);
-            const uint8_t* ref = (const uint8_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)s.ref, r);
-            const uint32_t* rovf = (const uint32_t*)__shfl_sync(0xFFFFFFFFu, (unsigned long long)ovf, r);
-            const int mbw = __shfl_sync(0xFFFFFFFFu, s.mbw, r);
-            const bool intra_r = (info >> 1) & 1;
-            const int cbp = (info >> 2) & 63, n1m = (info >> 8) & 63, abm = (info >> 14) & 63;
-            const int mx = (info >> 20) & 31, my = (info >> 25) & 15;
-            const int entries = cntw & 0xFFFF, skip_before = cntw >> 16;
-            const int live = cbp & ~abm;
-
-            const int mvh = (int)(int16_t)(mvw & 0xFFFF), mvv = (int)(int16_t)(mvw >> 16);
-            const int tile = ef_tile_offset(mx, my);
-
-            // ---- prediction loads first: 8 luma pixels per lane, 8 chroma pixels for lanes 0..15 ---
-            const int hx = mx * 32 + mvh, hy = my * 32 + mvv;                       // predict(), player.cpp:882
-            const int cx = hx >> 1, cy = hy >> 1;                                   // Q3: floor
-            const int lx = (hx >> 1) + phalf * 8, ly = (hy >> 1) + prow;
-            const int kx = cx >> 1, ky = (cy >> 1) + crow;
-            const int X0 = hx >> 1, Y0 = hy >> 1, tx0 = X0 >> 4, ty0 = Y0 >> 4;
-            // whole prediction window inside the picture (always, for streams the reference accepts)
-            const bool inside = hx >= 0 && hy >= 0 && X0 + 16 + (hx & 1) <= EF_W && Y0 + 16 + (hy & 1) <= EF_H;
-            if (!intra_r && inside && lane == 0) {
-                const bool two_x = ((X0 + 15 + (hx & 1)) >> 4) != tx0, two_y = ((Y0 + 15 + (hy & 1)) >> 4) != ty0;
-                const uint8_t* src = ref + ef_tile_offset(tx0, ty0);
-                // (the staging area is only ever written by these copies and read with plain loads that have
-                // all completed before the __syncwarp() that ended the previous macroblock)
-                const uint32_t row_bytes = two_x ? 2 * EF_TILE : EF_TILE;           // tiles of one row are contiguous in HBM
-                mbar_expect_tx(sbar, row_bytes << (int)two_y);
-                bulk_tiles(sstage, src, row_bytes, sbar);
-                if (two_y) bulk_tiles(sstage + 2 * EF_TILE, src + EF_MBW_MAX * EF_TILE, row_bytes, sbar);
-            }
-
-            // expand the coefficient list into the dense scratch
-            const uint32_t* rl = (const uint32_t*)wbase + r * kListEntries;
-            for (int j = lane; j < entries; j += 32) {
-                const uint32_t ent = j < kListEntries ? rl[j] : rovf[j - kListEntries];
-                const int eb = (ent >> 24) & 7;
-                if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((ent >> 18) & 63)] = ((int)(ent << 14)) >> 14;   // 18-bit signed value
-            }
-
-            // skipped macroblocks: predict_zero() copies them from the reference frame (player.cpp:1283-1288)
-            if (skip_before) {
-                int sx = mx, sy = my;
-                for (int k = 0; k < skip_before; k++) {
-                    if (--sx < 0) { sx = mbw - 1; sy--; }
-                    if (sy < 0) break;
-                    const int to = ef_tile_offset(sx, sy);
-                    if (lane < 24) *(uint4*)(cur + to + lane * 16) = *(const uint4*)(ref + to + lane * 16);
-                }
-            }
-            __syncwarp();                                                           // dense[] complete
-
-            // ---- residual: luma set (blocks 0-3), then chroma set (blocks 4,5) ---------------------
-            const int* dcs = (const int*)(H + kHdrDc);
-            int resY[8], resC[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) { resY[i] = 0; resC[i] = 0; }
-
-#pragma unroll
-            for (int set = 0; set < 2; set++) {
-                const int setmask = set == 0 ? 0x0F : 0x30;
-                if (!(live & setmask)) continue;                         // warp-uniform
-                const int bk = set == 0 ? cblk : 4 + (cblk & 1);
-                const bool lane_on = set == 0 || lane < 16;
-                // column pass, in place: lane (block, column) owns the 8 words dense[block][0..7][column]
-                if (lane_on) {
-                    int* db = dense + bk * kDenseStride + col;
-                    int v[8];
-#pragma unroll
-                    for (int rr = 0; rr < 8; rr++) v[rr] = db[rr * 8];
-                    if (intra_r && col == 0) v[0] = (int)((uint32_t)dcs[bk] << 8);      // b[0] <<= 8, player.cpp:1065
-                    idct8<false>(v);
-#pragma unroll
-                    for (int rr = 0; rr < 8; rr++) db[rr * 8] = v[rr];
-                }
-                __syncwarp();
-                // row pass: luma lanes own (rblk, rrow); chroma lanes 0..15 own (4 + lane/8, lane%8)
-                const int orow = set == 0 ? rrow : crow;
-                const int oblk = set == 0 ? rblk : 4 + cplane;
-                const bool ocoded = lane_on && (live >> oblk) & 1;
-                int w[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) w[i] = 0;
-                if (lane_on) {
-                    int4* rowp = (int4*)(dense + oblk * kDenseStride + orow * 8);
-                    const int4 a = rowp[0], b = rowp[1];
-                    rowp[0] = make_int4(0, 0, 0, 0); rowp[1] = make_int4(0, 0, 0, 0);    // leave the scratch zeroed for the next macroblock
-                    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-                }
-                if (ocoded) {
-                    if (!((n1m >> oblk) & 1)) idct8<true>(w);
-                    else {                                               // n == 1: dc = b[0] >> 8 (Q5); after the column pass every row holds b[0] in column 0
-                        const int dc = intra_r ? dcs[oblk] : w[0] >> 8;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] = dc;
-                    }
-                }
-                if (set == 0) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) resY[i] = w[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) resC[i] = w[i];
-                }
-                __syncwarp();
-            }
-
-            // ---- finish the prediction, combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
-            uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
-            if (!intra_r) {
-                PredWords wy, wc;
-                if (inside) {
-                    mbar_wait(sbar, bar_phase);
-                    bar_phase ^= 1;
-                    pred_words_staged<true>(stage, 0, lx, ly, tx0, ty0, hy & 1, wy);
-                    if (lane < 16) pred_words_staged<false>(stage, cplane, kx, ky, tx0, ty0, cy & 1, wc);
-                } else {
-                    pred_words_clamped<true>(ref, 0, lx, ly, hy & 1, wy);
-                    if (lane < 16) pred_words_clamped<false>(ref, cplane, kx, ky, cy & 1, wc);
-                }
-                pred_finish(wy, lx, hx & 1, hy & 1, py0, py1);
-                if (lane < 16) pred_finish(wc, kx, cx & 1, cy & 1, pc0, pc1);
-            }
-            {
-                const bool coded = (cbp >> rblk) & 1, aborted = (abm >> rblk) & 1, n1 = (n1m >> rblk) & 1;
-                uint32_t o0 = py0, o1 = py1;
-                bool store = true;
-                if (coded && !aborted) {
-                    if (intra_r && n1) {                                 // copy_block_dc: replicated, not clamped (Q7)
-                        uint32_t d = (uint32_t)resY[0]; d |= d << 8; d |= d << 16;
-                        o0 = o1 = d;
-                    } else {
-                        o0 = pin4(py0, resY[0], resY[1], resY[2], resY[3]);
-                        o1 = pin4(py1, resY[4], resY[5], resY[6], resY[7]);
-                    }
-                } else if (intra_r) store = false;                        // aborted intra block: destination untouched
-                if (store) *(uint2*)(cur + tile + prow * 16 + phalf * 8) = make_uint2(o0, o1);
-            }
-            if (lane < 16) {
-                const int bk = 4 + cplane;
-                const bool coded = (cbp >> bk) & 1, aborted = (abm >> bk) & 1, n1 = (n1m >> bk) & 1;
-                uint32_t o0 = pc0, o1 = pc1;
-                bool store = true;
-                if (coded && !aborted) {
-                    if (intra_r && n1) {
-                        uint32_t d = (uint32_t)resC[0]; d |= d << 8; d |= d << 16;
-                        o0 = o1 = d;
-                    } else {
-                        o0 = pin4(pc0, resC[0], resC[1], resC[2], resC[3]);
-                        o1 = pin4(pc1, resC[4], resC[5], resC[6], resC[7]);
-                    }
-                } else if (intra_r) store = false;
-                if (store) *(uint2*)(cur + tile + 256 + cplane * 64 + crow * 8) = make_uint2(o0, o1);
-            }
-
-            __syncwarp();
+            const uint64_t li = (uint64_t)(list0 - D.coef);
+            *(uint4*)rec = make_uint4((uint32_t)(s.wptr - list0) | (skipw << 16), mvw, (uint32_t)li, (uint32_t)(li >> 32));
+            D.mb_info[slot] = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp_all << 2) | ((uint32_t)n1mask << 8) |
+                              ((uint32_t)abortmask << 14) | ((uint32_t)s.mbw << 20);
         }
     }
 }
 
-// host-side launch helper ------------------------------------------------------------------------
-size_t ef_decode_smem_bytes() { return (size_t)kTableBytes + (size_t)kWarpsPerCta * kWarpBytes; }
-int ef_decode_threads() { return kWarpsPerCta * 32; }
+// =================================================================================================
+// K1b: macroblock records -> pixels, one warp per macroblock, one launch per picture index
+// =================================================================================================
+__global__ void __launch_bounds__(kReconWarps * 32, kReconCtasPerSm)
+ef_recon_kernel(const EfDev* __restrict__ Dp, int pic, int pic_rel)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const EfDev& D = *Dp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* wbase = smem + (size_t)warp * kWarpBytes;
+    int* dense = (int*)wbase;
+    uint8_t* stage = wbase + kDenseBytes;
+    uint64_t* bar = (uint64_t*)(stage + kStageBytes);
+    const uint32_t sstage = smem_u32(stage), sbar = smem_u32(bar);
+    uint32_t bar_phase = 0;
+    if (lane == 0) mbar_init(bar, 1);
+    for (int i = lane; i < kDenseBytes / 4; i += 32) ((uint32_t*)dense)[i] = 0;
+    __syncwarp();
+
+    constexpr uint32_t kMbs = EF_MBW_MAX * EF_MBH_MAX;
+    const uint32_t n_slots = (uint32_t)D.n_streams * kMbs;
+    const uint32_t* infos = D.mb_info + (size_t)pic_rel * n_slots;
+    const EfMbRec* recs = D.mb_rec + (size_t)pic_rel * n_slots;
+    const uint32_t nw = gridDim.x * kReconWarps;
+
+    // per-lane constants of the reconstruction mapping
+    const int col = lane & 7;                       // column owned in the IDCT column pass
+    const int cblk = lane >> 3;                     // block (0..3) owned in the column pass
+    const int prow = lane >> 1, phalf = lane & 1;   // luma pixel row / 8-pixel half owned for prediction + store
+    const int rblk = (prow >> 3) * 2 + phalf;       // block that those pixels belong to
+    const int rrow = prow & 7;                      // row of that block
+    const int crow = lane & 7, cplane = (lane >> 3) & 1;   // chroma row / plane owned by lanes 0..15
+
+    // one load per lane fetches a whole record: lanes 0-9 its words, lane 12 the info word, lane 13 the
+    // ping-pong phase of the stream
+    auto fetch = [&](uint32_t slot) -> uint32_t {
+        if (slot >= n_slots) return 0u;
+        if (lane < 10) return ((const uint32_t*)(recs + slot))[lane];
+        if (lane == 12) return infos[slot];
+        if (lane == 13) return D.base_pics[slot / kMbs];
+        return 0u;
+    };
+
+    uint32_t slot = blockIdx.x * kReconWarps + warp;
+    uint32_t pre = fetch(slot);
+    for (; slot < n_slots; slot += nw) {
+        const uint32_t recw = pre;
+        pre = fetch(slot + nw);
+        const uint32_t info = __shfl_sync(0xFFFFFFFFu, recw, 12);
+        if (!(info & 1u)) continue;
+        const uint32_t cntw = __shfl_sync(0xFFFFFFFFu, recw, 0);
+        const uint32_t mvw = __shfl_sync(0xFFFFFFFFu, recw, 1);
+        const uint64_t li = (uint64_t)__shfl_sync(0xFFFFFFFFu, recw, 2) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, recw, 3) << 32);
+        const uint32_t base_pics = __shfl_sync(0xFFFFFFFFu, recw, 13);
+        const uint32_t stream = slot / kMbs, mb = slot - stream * kMbs;
+        const int my = (int)(mb / EF_MBW_MAX), mx = (int)(mb - (uint32_t)my * EF_MBW_MAX);
+        const uint32_t fb = (base_pics + (uint32_t)pic + 1u) & 1u;                  // flush_picture(), player.cpp:692
+        uint8_t* cur = D.frames + ef_frame_offset((int)stream, (int)fb);
+        const uint8_t* ref = D.frames + ef_frame_offset((int)stream, (int)(fb ^ 1u));
+        const bool intra_r = (info >> 1) & 1;
+        const int cbp = (info >> 2) & 63, n1m = (info >> 8) & 63, abm = (info >> 14) & 63;
+        const int mbw = (info >> 20) & 31;
+        const int entries = min((int)(cntw & 0xFFFF), 384), skip_before = cntw >> 16;
+        const int live = cbp & ~abm;
+
+        // coefficient list: issue the loads first
+        const uint32_t* rl = D.coef + li;
+        uint32_t e0 = 0, e1 = 0;
+        if (lane < entries) e0 = __ldg(rl + lane);
+        if (lane + 32 < entries) e1 = __ldg(rl + lane + 32);
+
+        const int mvh = (int)(int16_t)(mvw & 0xFFFF), mvv = (int)(int16_t)(mvw >> 16);
+        const int tile = ef_tile_offset(mx, my);
+
+        // ---- prediction: 8 luma pixels per lane, 8 chroma pixels for lanes 0..15 ---------------
+        const int hx = mx * 32 + mvh, hy = my * 32 + mvv;                       // predict(), player.cpp:882
+        const int cx = hx >> 1, cy = hy >> 1;                                   // Q3: floor
+        const int lx = (hx >> 1) + phalf * 8, ly = (hy >> 1) + prow;
+        const int kx = cx >> 1, ky = (cy >> 1) + crow;
+        const int X0 = hx >> 1, Y0 = hy >> 1, tx0 = X0 >> 4, ty0 = Y0 >> 4;
+        // whole prediction window inside the picture (always, for streams the reference accepts)
+        const bool inside = hx >= 0 && hy >= 0 && X0 + 16 + (hx & 1) <= EF_W && Y0 + 16 + (hy & 1) <= EF_H;
+        if (!intra_r && inside && lane == 0) {
+            const bool two_x = ((X0 + 15 + (hx & 1)) >> 4) != tx0, two_y = ((Y0 + 15 + (hy & 1)) >> 4) != ty0;
+            const uint8_t* src = ref + ef_tile_offset(tx0, ty0);
+            // (the staging area is only ever written by these copies and read with plain loads that have
+            // all completed before the __syncwarp() that ended the previous macroblock)
+            const uint32_t row_bytes = two_x ? 2 * EF_TILE : EF_TILE;           // tiles of one row are contiguous in HBM
+            mbar_expect_tx(sbar, row_bytes << (int)two_y);
+            bulk_tiles(sstage, src, row_bytes, sbar);
+            if (two_y) bulk_tiles(sstage + 2 * EF_TILE, src + EF_MBW_MAX * EF_TILE, row_bytes, sbar);
+        }
+
+        // skipped macroblocks: predict_zero() copies them from the reference frame (player.cpp:1283-1288)
+        if (skip_before) {
+            int sx = mx, sy = my;
+            for (int k = 0; k < skip_before; k++) {
+                if (--sx < 0) { sx = mbw - 1; sy--; }
+                if (sy < 0) break;
+                const int to = ef_tile_offset(sx, sy);
+                if (lane < 24) *(uint4*)(cur + to + lane * 16) = *(const uint4*)(ref + to + lane * 16);
+            }
+        }
+
+        // expand the coefficient list into the dense scratch (entries of aborted blocks are dropped;
+        // block numbers 6, 7 can only come from a damaged record and land in the dump blocks)
+        if (lane < entries) { const int eb = (e0 >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((e0 >> 18) & 63)] = ((int)(e0 << 14)) >> 14; }
+        if (lane + 32 < entries) { const int eb = (e1 >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((e1 >> 18) & 63)] = ((int)(e1 << 14)) >> 14; }
+        for (int j = lane + 64; j < entries; j += 32) {
+            const uint32_t ent = __ldg(rl + j);
+            const int eb = (ent >> 24) & 7;
+            if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((ent >> 18) & 63)] = ((int)(ent << 14)) >> 14;   // 18-bit signed value
+        }
+        __syncwarp();                                                           // dense[] complete
+
+        // ---- residual: luma set (blocks 0-3), then chroma set (blocks 4,5) ---------------------
+        int resY[8], resC[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { resY[i] = 0; resC[i] = 0; }
+
+#pragma unroll
+        for (int set = 0; set < 2; set++) {
+            const int setmask = set == 0 ? 0x0F : 0x30;
+            if (!(live & setmask)) continue;                         // warp-uniform
+            const int bk = set == 0 ? cblk : 4 + (cblk & 1);
+            const bool lane_on = set == 0 || lane < 16;
+            const int orow = set == 0 ? rrow : crow;
+            const int oblk = set == 0 ? rblk : 4 + cplane;
+            const int dc_col = (int)__shfl_sync(0xFFFFFFFFu, recw, 4 + bk);      // intra DC of the block this lane owns in the column pass
+            const int dc_row = (int)__shfl_sync(0xFFFFFFFFu, recw, 4 + oblk);    // ... and in the row pass
+            // column pass, in place: lane (block, column) owns the 8 words dense[block][0..7][column]
+            if (lane_on) {
+                int* db = dense + bk * kDenseStride + col;
+                int v[8];
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) v[rr] = db[rr * 8];
+                if (intra_r && col == 0) v[0] = (int)((uint32_t)dc_col << 8);       // b[0] <<= 8, player.cpp:1065
+                idct8<false>(v);
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) db[rr * 8] = v[rr];
+            }
+            __syncwarp();
+            // row pass: luma lanes own (rblk, rrow); chroma lanes 0..15 own (4 + lane/8, lane%8)
+            const bool ocoded = lane_on && (live >> oblk) & 1;
+            int w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = 0;
+            if (lane_on) {
+                int4* rowp = (int4*)(dense + oblk * kDenseStride + orow * 8);
+                const int4 a = rowp[0], b = rowp[1];
+                rowp[0] = make_int4(0, 0, 0, 0); rowp[1] = make_int4(0, 0, 0, 0);    // leave the scratch zeroed for the next macroblock
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            }
+            if (ocoded) {
+                if (!((n1m >> oblk) & 1)) idct8<true>(w);
+                else {                                               // n == 1: dc = b[0] >> 8 (Q5); after the column pass every row holds b[0] in column 0
+                    const int dc = intra_r ? dc_row : w[0] >> 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) w[i] = dc;
+                }
+            }
+            if (set == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) resY[i] = w[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) resC[i] = w[i];
+            }
+            __syncwarp();
+        }
+
+        // ---- finish the prediction, combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
+        uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
+        if (!intra_r) {
+            PredWords wy, wc;
+            if (inside) {
+                mbar_wait(sbar, bar_phase);
+                bar_phase ^= 1;
+                pred_words_staged<true>(stage, 0, lx, ly, tx0, ty0, hy & 1, wy);
+                if (lane < 16) pred_words_staged<false>(stage, cplane, kx, ky, tx0, ty0, cy & 1, wc);
+            } else {
+                pred_words_clamped<true>(ref, 0, lx, ly, hy & 1, wy);
+                if (lane < 16) pred_words_clamped<false>(ref, cplane, kx, ky, cy & 1, wc);
+            }
+            pred_finish(wy, lx, hx & 1, hy & 1, py0, py1);
+            if (lane < 16) pred_finish(wc, kx, cx & 1, cy & 1, pc0, pc1);
+        }
+        {
+            const bool coded = (cbp >> rblk) & 1, aborted = (abm >> rblk) & 1, n1 = (n1m >> rblk) & 1;
+            uint32_t o0 = py0, o1 = py1;
+            bool store = true;
+            if (coded && !aborted) {
+                if (intra_r && n1) {                                 // copy_block_dc: replicated, not clamped (Q7)
+                    uint32_t d = (uint32_t)resY[0]; d |= d << 8; d |= d << 16;
+                    o0 = o1 = d;
+                } else {
+                    o0 = pin4(py0, resY[0], resY[1], resY[2], resY[3]);
+                    o1 = pin4(py1, resY[4], resY[5], resY[6], resY[7]);
+                }
+            } else if (intra_r) store = false;                        // aborted intra block: destination untouched
+            if (store) *(uint2*)(cur + tile + prow * 16 + phalf * 8) = make_uint2(o0, o1);
+        }
+        if (lane < 16) {
+            const int bk = 4 + cplane;
+            const bool coded = (cbp >> bk) & 1, aborted = (abm >> bk) & 1, n1 = (n1m >> bk) & 1;
+            uint32_t o0 = pc0, o1 = pc1;
+            bool store = true;
+            if (coded && !aborted) {
+                if (intra_r && n1) {
+                    uint32_t d = (uint32_t)resC[0]; d |= d << 8; d |= d << 16;
+                    o0 = o1 = d;
+                } else {
+                    o0 = pin4(pc0, resC[0], resC[1], resC[2], resC[3]);
+                    o1 = pin4(pc1, resC[4], resC[5], resC[6], resC[7]);
+                }
+            } else if (intra_r) store = false;
+            if (store) *(uint2*)(cur + tile + 256 + cplane * 64 + crow * 8) = make_uint2(o0, o1);
+        }
+
+        __syncwarp();
+    }
+}
+
+// host-side launch helpers -----------------------------------------------------------------------
+size_t ef_recon_smem_bytes() { return (size_t)kReconWarps * kWarpBytes; }
 
 cudaError_t ef_decode_configure()
 {
-    return cudaFuncSetAttribute(ef_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ef_decode_smem_bytes());
+    return cudaFuncSetAttribute(ef_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ef_recon_smem_bytes());
 }
 
-cudaError_t ef_launch_decode(const EfDev* dev, int pic, int ctas, cudaStream_t stream)
+// parse every slice of picture indices [pic0, pic0 + n_pics) into record pictures 0 .. n_pics-1
+cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream)
 {
-    ef_decode_kernel<<<ctas, kWarpsPerCta * 32, ef_decode_smem_bytes(), stream>>>(dev, pic);
+    ef_parse_kernel<<<sm_count * kParseCtasPerSm, kParseThreads, 0, stream>>>(dev, pic0, n_pics);
+    return cudaGetLastError();
+}
+
+// rebuild picture index `pic` of every stream from record picture `pic_rel`
+cudaError_t ef_launch_recon(const EfDev* dev, int pic, int pic_rel, int sm_count, cudaStream_t stream)
+{
+    ef_recon_kernel<<<sm_count * kReconCtasPerSm, kReconWarps * 32, ef_recon_smem_bytes(), stream>>>(dev, pic, pic_rel);
     return cudaGetLastError();
 }

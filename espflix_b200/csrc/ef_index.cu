@@ -237,7 +237,7 @@ ef_fill_kernel(EfDev* __restrict__ Dp)
         w.stream = (uint32_t)s;
         w.es_off = D.slice_off[(size_t)s * D.max_slices + first + j];
         w.info = (uint32_t)D.slice_code[(size_t)s * D.max_slices + first + j] | (type << 8) | ((uint32_t)(pic.fp_rsize & 15) << 11) | (seq_idx << 16);
-        w.pad = 0;
+        w.pic = (uint32_t)p;
         D.work[dst + j] = w;
     }
 }
