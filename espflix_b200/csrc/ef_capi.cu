@@ -9,6 +9,7 @@
 
 #include "../../include/espflix_b200.h"
 #include "ef_common.cuh"
+#include <stdlib.h>
 
 // from the other translation units
 int ef_build_tables(EfTables* t);
@@ -24,8 +25,9 @@ __global__ void ef_ts_copy_kernel(const uint8_t* ts, uint64_t n_packets, const u
 __global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint64_t* off, const uint64_t* ts_off, int n_streams, uint64_t* es_off, uint8_t* es);
 size_t ef_recon_smem_bytes();
 cudaError_t ef_decode_configure();
+int ef_decode_resident_ctas(int which);
 cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream);
-cudaError_t ef_launch_recon(const EfDev* dev, int pic, int pic_rel, int sm_count, cudaStream_t stream);
+cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, cudaStream_t stream);
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream);
 cudaError_t ef_launch_blit(const EfDev* dev, int stream_index, int fb, int line, int x, int width, int frame_counter, uint16_t* dst, cudaStream_t stream);
 
@@ -199,6 +201,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
         return fail(EF_ECUDA, "device offers %zu B shared memory per CTA, kernel needs %zu", (size_t)prop.sharedMemPerBlockOptin, ef_recon_smem_bytes());
     }
     CK(ef_decode_configure());
+    if (getenv("EF_VERBOSE")) fprintf(stderr, "espflix_b200: %d SMs, resident CTAs per SM: parse %d, reconstruct %d\n", c->sm_count, ef_decode_resident_ctas(0), ef_decode_resident_ctas(1));
     CK(ef_index_upload_constants());
 
     const int n = cfg->n_streams;
@@ -234,13 +237,14 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     A(h.work, h.work_capacity);
     A(h.info, 8);
     EfTables* dt; A(dt, 1);
-    A(h.parse_cursor, 4);
     {   // macroblock records: as many picture indices per K1a launch as fit in 2 GiB
         const size_t per_pic = (size_t)n * EF_MBW_MAX * EF_MBH_MAX * (sizeof(EfMbRec) + 4);
         size_t k = ((size_t)2 << 30) / per_pic;
         h.rec_pics = (int)(k < 1 ? 1 : k > (size_t)h.max_pictures ? (size_t)h.max_pictures : k);
         const size_t slots = (size_t)h.rec_pics * n * EF_MBW_MAX * EF_MBH_MAX;
         A(h.mb_info, slots); A(h.mb_rec, slots);
+        A(h.parse_cursor, (size_t)h.rec_pics + 4);      // [0] K1a, [1..] one per K1b launch
+        h.recon_cursor = h.parse_cursor + 1;
         A(h.coef, 3 * (cfg->es_capacity + 1024) + 1024);
     }
     A(c->d_color_tab, 768); A(c->d_pal_burst, 128); A(c->d_default_intra, 64); A(c->d_overlay, 1280);
@@ -425,9 +429,9 @@ static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st)
 {
     const size_t slots = (size_t)k * c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX;
     CK(cudaMemsetAsync(c->h.mb_info, 0, slots * 4, st));
-    CK(cudaMemsetAsync(c->h.parse_cursor, 0, 4, st));
+    CK(cudaMemsetAsync(c->h.parse_cursor, 0, ((size_t)k + 1) * 4, st));
     CK(ef_launch_parse(c->d, p0, k, c->sm_count, st));
-    for (int i = 0; i < k; i++) CK(ef_launch_recon(c->d, p0 + i, i, c->sm_count, st));
+    for (int i = 0; i < k; i++) CK(ef_launch_recon(c->d, i, c->sm_count, st));
     CK(cudaEventRecord(c->ev_buf_free[c->active], st));     // the front ES buffer is in use until here
     c->launches += 1 + (uint64_t)k;
     return EF_OK;

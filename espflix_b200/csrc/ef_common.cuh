@@ -132,6 +132,7 @@ struct EfDev {               // device-visible context (lives in device memory)
     uint32_t* pic_base;      // [max_pictures] start of that picture's range in `work`
     uint32_t* cursor;        // [max_pictures] (kept for the index kernels)
     uint32_t* parse_cursor;  // work-stealing cursor of K1a, zeroed before every launch
+    uint32_t* recon_cursor;  // [rec_pics] work cursors of the K1b launches, zeroed with it
     EfWork* work;            // flat, grouped by picture index
     uint32_t* info;          // [8]: 0 max pictures, 1 total pictures, 2 total slices, 3 error flags
     const EfTables* tables;

@@ -42,11 +42,12 @@ constexpr int kReconWarps = EF_K1B_WARPS;       // per CTA
 constexpr int kReconCtasPerSm = EF_K1B_CTAS;
 
 // macroblock info word (EfDev::mb_info): bit0 valid, 1 intra, 2-7 coded blocks, 8-13 n==1 mask,
-// 14-19 abort mask (bit b = block b), 20-24 mb_width of the stream
+// 14-19 abort mask (bit b = block b), 20-24 mb_width of the stream, 25 destination frame store
 constexpr int kDenseStride = 72;                // words per block in the dense scratch: 64 + 8 pad -> the 4 luma blocks hit distinct banks
-constexpr int kDenseBytes = 8 * kDenseStride * 4;   // int32 [6][72] prescaled coefficients, raster order, also the IDCT transpose buffer; + 2 dump blocks for malformed entries
+constexpr int kDenseWords = 6 * kDenseStride;   // int32 [6][72] prescaled coefficients, raster order, also the IDCT transpose buffer; 432 = 16 mod 32: the two halves of a warp hit disjoint banks
+constexpr int kDenseBytes = kDenseWords * 4;
 constexpr int kStageBytes = 4 * EF_TILE;        // motion-compensation staging: up to 2 x 2 reference tiles per macroblock
-constexpr int kWarpBytes = kDenseBytes + kStageBytes + 16;   // + the warp's mbarrier
+constexpr int kWarpBytes = 2 * (kDenseBytes + kStageBytes) + 16;   // two macroblocks per warp + their mbarriers
 
 struct SharedTables {                           // same layout as the head of EfTables
     uint16_t dct[26 * 32];
@@ -104,7 +105,7 @@ struct BitReader {
 struct SliceState {
     BitReader br;
     uint32_t* wptr;          // next free entry of this slice's coefficient list in HBM
-    uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture
+    uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture | destination frame store << 31
     const uint8_t* qtab;     // scan-order quantiser tables [intra 64 | non-intra 64]: the shared-memory defaults or the stream's own in HBM
     int mbw, mbh;
     int mb_x, mb_y;          // last macroblock handled
@@ -457,6 +458,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                     s.qtab = seq->custom ? (const uint8_t*)seq->q_scan : (const uint8_t*)T.qdef;
                     const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
                     s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
+                    s.slot_base |= ((D.base_pics[w.stream] + w.pic + 1u) & 1u) << 31;      // destination frame store: flush_picture(), player.cpp:692
                     s.wptr = D.coef + 3 * byte_off;          // >= 3 bits of bitstream per coefficient: lists cannot collide
                     s.br.init(D.es, byte_off);
                     s.mb_y = code - 2; s.mb_x = s.mbw - 1;   // slice(), player.cpp:1255: the first increment lands on column 0 of row code-1
@@ -481,7 +483,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
             if (!have) active = false;
         }
         const int cbp_all = cbp_rem;
-        const uint32_t slot = s.slot_base + (uint32_t)(s.mb_y * EF_MBW_MAX + s.mb_x);
+        const uint32_t slot = (s.slot_base & 0x7FFFFFFFu) + (uint32_t)(s.mb_y * EF_MBW_MAX + s.mb_x);
         EfMbRec* rec = D.mb_rec + slot;
         uint32_t* const list0 = s.wptr;
 
@@ -542,99 +544,106 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
             const uint64_t li = (uint64_t)(list0 - D.coef);
             *(uint4*)rec = make_uint4((uint32_t)(s.wptr - list0) | (skipw << 16), mvw, (uint32_t)li, (uint32_t)(li >> 32));
             D.mb_info[slot] = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp_all << 2) | ((uint32_t)n1mask << 8) |
-                              ((uint32_t)abortmask << 14) | ((uint32_t)s.mbw << 20);
+                              ((uint32_t)abortmask << 14) | ((uint32_t)s.mbw << 20) | ((s.slot_base >> 31) << 25);
         }
     }
 }
 
 // =================================================================================================
-// K1b: macroblock records -> pixels, one warp per macroblock, one launch per picture index
+// K1b: macroblock records -> pixels, one launch per picture index. A HALF-WARP rebuilds one
+// macroblock (a warp = two consecutive macroblock slots): its 48 eight-pixel row segments are 3 passes
+// of 16 lanes, so every lane is busy in every pass, and the per-macroblock bookkeeping (record decode,
+// TMA issue, list expansion) is paid once per two macroblocks.
+//   lane hl = lane & 15 of a half:  column pass p (p = 0..2): block 2p + hl/8, column hl%8
+//                                   row pass 0, 1: luma row 8p + hl/2, 8-pixel half hl%2 (block 2p + hl%2)
+//                                   row pass 2:    chroma plane hl/8 (block 4 + hl/8), row hl%8
 // =================================================================================================
 __global__ void __launch_bounds__(kReconWarps * 32, kReconCtasPerSm)
-ef_recon_kernel(const EfDev* __restrict__ Dp, int pic, int pic_rel)
+ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const EfDev& D = *Dp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hl = lane & 15, hb = lane & 16, half = lane >> 4;
     uint8_t* wbase = smem + (size_t)warp * kWarpBytes;
-    int* dense = (int*)wbase;
-    uint8_t* stage = wbase + kDenseBytes;
-    uint64_t* bar = (uint64_t*)(stage + kStageBytes);
+    int* dense = (int*)wbase + half * kDenseWords;
+    uint8_t* stage = wbase + 2 * kDenseBytes + half * kStageBytes;
+    uint64_t* bar = (uint64_t*)(wbase + 2 * kDenseBytes + 2 * kStageBytes) + half;
     const uint32_t sstage = smem_u32(stage), sbar = smem_u32(bar);
     uint32_t bar_phase = 0;
-    if (lane == 0) mbar_init(bar, 1);
-    for (int i = lane; i < kDenseBytes / 4; i += 32) ((uint32_t*)dense)[i] = 0;
+    if (hl == 0) mbar_init(bar, 1);
+    for (int i = hl; i < kDenseWords; i += 16) dense[i] = 0;
     __syncwarp();
 
     constexpr uint32_t kMbs = EF_MBW_MAX * EF_MBH_MAX;
-    const uint32_t n_slots = (uint32_t)D.n_streams * kMbs;
+    const uint32_t n_slots = (uint32_t)D.n_streams * kMbs;            // even
     const uint32_t* infos = D.mb_info + (size_t)pic_rel * n_slots;
-    const EfMbRec* recs = D.mb_rec + (size_t)pic_rel * n_slots;
-    const uint32_t nw = gridDim.x * kReconWarps;
+    const uint32_t* recs = (const uint32_t*)(D.mb_rec + (size_t)pic_rel * n_slots);
 
-    // per-lane constants of the reconstruction mapping
-    const int col = lane & 7;                       // column owned in the IDCT column pass
-    const int cblk = lane >> 3;                     // block (0..3) owned in the column pass
-    const int prow = lane >> 1, phalf = lane & 1;   // luma pixel row / 8-pixel half owned for prediction + store
-    const int rblk = (prow >> 3) * 2 + phalf;       // block that those pixels belong to
-    const int rrow = prow & 7;                      // row of that block
-    const int crow = lane & 7, cplane = (lane >> 3) & 1;   // chroma row / plane owned by lanes 0..15
+    const int ccol = hl & 7, cpb = hl >> 3;         // column pass: column, block within the pair
+    const int prow = hl >> 1, phalf = hl & 1;       // luma row passes
+    const int crow = hl & 7, cplane = hl >> 3;      // chroma row pass
 
-    // one load per lane fetches a whole record: lanes 0-9 its words, lane 12 the info word, lane 13 the
-    // ping-pong phase of the stream
+    // one load per lane fetches a record: lanes 0-9 of the half its words, lane 12 the info word
     auto fetch = [&](uint32_t slot) -> uint32_t {
-        if (slot >= n_slots) return 0u;
-        if (lane < 10) return ((const uint32_t*)(recs + slot))[lane];
-        if (lane == 12) return infos[slot];
-        if (lane == 13) return D.base_pics[slot / kMbs];
-        return 0u;
+        uint32_t v = 0;
+        if (slot < n_slots && (hl < 10 || hl == 12)) v = __ldg(hl == 12 ? infos + slot : recs + (size_t)slot * (sizeof(EfMbRec) / 4) + hl);
+        return v;
     };
 
-    uint32_t slot = blockIdx.x * kReconWarps + warp;
-    uint32_t pre = fetch(slot);
-    for (; slot < n_slots; slot += nw) {
+    // Work distribution: the first two pairs of a warp are static, later ones come from a global cursor
+    // (the warp schedulers do not share the issue slots evenly, so a static split leaves a long tail). The
+    // atomic is issued two iterations ahead of its use and the record one iteration ahead.
+    const uint32_t n_warps = gridDim.x * kReconWarps;
+    uint32_t* cursor = D.recon_cursor + pic_rel;
+    uint32_t pair = blockIdx.x * kReconWarps + warp, pair_next = pair + n_warps, pair_fut = 0;
+    uint32_t pre = fetch(pair * 2 + half);
+    for (;; pair = pair_next, pair_next = __shfl_sync(0xFFFFFFFFu, pair_fut, 0)) {
+        if (pair * 2 >= n_slots) break;
+        const uint32_t slot = pair * 2 + half;
         const uint32_t recw = pre;
-        pre = fetch(slot + nw);
-        const uint32_t info = __shfl_sync(0xFFFFFFFFu, recw, 12);
-        if (!(info & 1u)) continue;
-        const uint32_t cntw = __shfl_sync(0xFFFFFFFFu, recw, 0);
-        const uint32_t mvw = __shfl_sync(0xFFFFFFFFu, recw, 1);
-        const uint64_t li = (uint64_t)__shfl_sync(0xFFFFFFFFu, recw, 2) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, recw, 3) << 32);
-        const uint32_t base_pics = __shfl_sync(0xFFFFFFFFu, recw, 13);
+        pre = fetch(pair_next * 2 + half);
+        if (lane == 0) pair_fut = 2 * n_warps + atomicAdd(cursor, 1u);
+        const uint32_t info = __shfl_sync(0xFFFFFFFFu, recw, hb + 12);
+        const bool valid = info & 1u;
+        if (!__any_sync(0xFFFFFFFFu, valid)) continue;
+        const uint32_t cntw = __shfl_sync(0xFFFFFFFFu, recw, hb);
+        const uint32_t mvw = __shfl_sync(0xFFFFFFFFu, recw, hb + 1);
+        const uint64_t li = (uint64_t)__shfl_sync(0xFFFFFFFFu, recw, hb + 2) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, recw, hb + 3) << 32);
         const uint32_t stream = slot / kMbs, mb = slot - stream * kMbs;
         const int my = (int)(mb / EF_MBW_MAX), mx = (int)(mb - (uint32_t)my * EF_MBW_MAX);
-        const uint32_t fb = (base_pics + (uint32_t)pic + 1u) & 1u;                  // flush_picture(), player.cpp:692
+        const uint32_t fb = (info >> 25) & 1u;                                      // flush_picture(), player.cpp:692
         uint8_t* cur = D.frames + ef_frame_offset((int)stream, (int)fb);
         const uint8_t* ref = D.frames + ef_frame_offset((int)stream, (int)(fb ^ 1u));
         const bool intra_r = (info >> 1) & 1;
-        const int cbp = (info >> 2) & 63, n1m = (info >> 8) & 63, abm = (info >> 14) & 63;
+        const int cbp = valid ? (info >> 2) & 63 : 0, n1m = (info >> 8) & 63;
+        const int abm = ((info >> 14) & 63) | 0xC0;                                 // block numbers 6, 7 (damaged record): dropped
         const int mbw = (info >> 20) & 31;
-        const int entries = min((int)(cntw & 0xFFFF), 384), skip_before = cntw >> 16;
+        const int entries = valid ? min((int)(cntw & 0xFFFF), 384) : 0, skip_before = valid ? (int)(cntw >> 16) : 0;
         const int live = cbp & ~abm;
+        const bool do_mc = valid && !intra_r;
 
         // coefficient list: issue the loads first
         const uint32_t* rl = D.coef + li;
-        uint32_t e0 = 0, e1 = 0;
-        if (lane < entries) e0 = __ldg(rl + lane);
-        if (lane + 32 < entries) e1 = __ldg(rl + lane + 32);
+        uint32_t e0 = 0, e1 = 0, e2 = 0;
+        if (hl < entries) e0 = __ldg(rl + hl);
+        if (hl + 16 < entries) e1 = __ldg(rl + hl + 16);
+        if (hl + 32 < entries) e2 = __ldg(rl + hl + 32);
 
         const int mvh = (int)(int16_t)(mvw & 0xFFFF), mvv = (int)(int16_t)(mvw >> 16);
         const int tile = ef_tile_offset(mx, my);
-
-        // ---- prediction: 8 luma pixels per lane, 8 chroma pixels for lanes 0..15 ---------------
         const int hx = mx * 32 + mvh, hy = my * 32 + mvv;                       // predict(), player.cpp:882
         const int cx = hx >> 1, cy = hy >> 1;                                   // Q3: floor
-        const int lx = (hx >> 1) + phalf * 8, ly = (hy >> 1) + prow;
-        const int kx = cx >> 1, ky = (cy >> 1) + crow;
         const int X0 = hx >> 1, Y0 = hy >> 1, tx0 = X0 >> 4, ty0 = Y0 >> 4;
         // whole prediction window inside the picture (always, for streams the reference accepts)
         const bool inside = hx >= 0 && hy >= 0 && X0 + 16 + (hx & 1) <= EF_W && Y0 + 16 + (hy & 1) <= EF_H;
-        if (!intra_r && inside && lane == 0) {
+        if (do_mc && inside && hl == 0) {
+            // reference tiles by TMA bulk copy: the prediction window lies in at most 2 x 2 tiles, tiles of
+            // one row are contiguous in HBM. (The staging area is only written by these copies and read with
+            // plain loads that have all completed before the __syncwarp() that ended the previous iteration.)
             const bool two_x = ((X0 + 15 + (hx & 1)) >> 4) != tx0, two_y = ((Y0 + 15 + (hy & 1)) >> 4) != ty0;
             const uint8_t* src = ref + ef_tile_offset(tx0, ty0);
-            // (the staging area is only ever written by these copies and read with plain loads that have
-            // all completed before the __syncwarp() that ended the previous macroblock)
-            const uint32_t row_bytes = two_x ? 2 * EF_TILE : EF_TILE;           // tiles of one row are contiguous in HBM
+            const uint32_t row_bytes = two_x ? 2 * EF_TILE : EF_TILE;
             mbar_expect_tx(sbar, row_bytes << (int)two_y);
             bulk_tiles(sstage, src, row_bytes, sbar);
             if (two_y) bulk_tiles(sstage + 2 * EF_TILE, src + EF_MBW_MAX * EF_TILE, row_bytes, sbar);
@@ -647,125 +656,97 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic, int pic_rel)
                 if (--sx < 0) { sx = mbw - 1; sy--; }
                 if (sy < 0) break;
                 const int to = ef_tile_offset(sx, sy);
-                if (lane < 24) *(uint4*)(cur + to + lane * 16) = *(const uint4*)(ref + to + lane * 16);
+                *(uint4*)(cur + to + hl * 16) = *(const uint4*)(ref + to + hl * 16);
+                *(uint2*)(cur + to + 256 + hl * 8) = *(const uint2*)(ref + to + 256 + hl * 8);
             }
         }
 
-        // expand the coefficient list into the dense scratch (entries of aborted blocks are dropped;
-        // block numbers 6, 7 can only come from a damaged record and land in the dump blocks)
-        if (lane < entries) { const int eb = (e0 >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((e0 >> 18) & 63)] = ((int)(e0 << 14)) >> 14; }
-        if (lane + 32 < entries) { const int eb = (e1 >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((e1 >> 18) & 63)] = ((int)(e1 << 14)) >> 14; }
-        for (int j = lane + 64; j < entries; j += 32) {
-            const uint32_t ent = __ldg(rl + j);
-            const int eb = (ent >> 24) & 7;
-            if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((ent >> 18) & 63)] = ((int)(ent << 14)) >> 14;   // 18-bit signed value
-        }
+        // expand the coefficient list into the dense scratch (entries of aborted blocks are dropped)
+#define EF_EXPAND(ent) { const int eb = ((ent) >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + (((ent) >> 18) & 63)] = ((int)((ent) << 14)) >> 14; }
+        if (hl < entries) EF_EXPAND(e0)
+        if (hl + 16 < entries) EF_EXPAND(e1)
+        if (hl + 32 < entries) EF_EXPAND(e2)
+        for (int j = hl + 48; j < entries; j += 16) { const uint32_t ent = __ldg(rl + j); EF_EXPAND(ent) }
+#undef EF_EXPAND
         __syncwarp();                                                           // dense[] complete
 
-        // ---- residual: luma set (blocks 0-3), then chroma set (blocks 4,5) ---------------------
-        int resY[8], resC[8];
+        // ---- column passes, in place: lane (block, column) owns the 8 words dense[block][0..7][column]
+        unsigned pass_on = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) { resY[i] = 0; resC[i] = 0; }
+        for (int p = 0; p < 3; p++) {
+            if (!__any_sync(0xFFFFFFFFu, live & (3 << (2 * p)))) continue;       // warp-uniform
+            pass_on |= 1u << p;
+            const int bk = 2 * p + cpb;
+            const int dc_col = (int)__shfl_sync(0xFFFFFFFFu, recw, hb + 4 + bk);  // intra DC of that block
+            int* db = dense + bk * kDenseStride + ccol;
+            int v[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) v[rr] = db[rr * 8];
+            if (intra_r && ccol == 0) v[0] = (int)((uint32_t)dc_col << 8);       // b[0] <<= 8, player.cpp:1065
+            idct8<false>(v);
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) db[rr * 8] = v[rr];
+        }
+        __syncwarp();
 
+        if (do_mc && inside) { mbar_wait(sbar, bar_phase); bar_phase ^= 1; }
+
+        // ---- row passes: residual row, prediction, clamped add, store ---------------------------------
 #pragma unroll
-        for (int set = 0; set < 2; set++) {
-            const int setmask = set == 0 ? 0x0F : 0x30;
-            if (!(live & setmask)) continue;                         // warp-uniform
-            const int bk = set == 0 ? cblk : 4 + (cblk & 1);
-            const bool lane_on = set == 0 || lane < 16;
-            const int orow = set == 0 ? rrow : crow;
-            const int oblk = set == 0 ? rblk : 4 + cplane;
-            const int dc_col = (int)__shfl_sync(0xFFFFFFFFu, recw, 4 + bk);      // intra DC of the block this lane owns in the column pass
-            const int dc_row = (int)__shfl_sync(0xFFFFFFFFu, recw, 4 + oblk);    // ... and in the row pass
-            // column pass, in place: lane (block, column) owns the 8 words dense[block][0..7][column]
-            if (lane_on) {
-                int* db = dense + bk * kDenseStride + col;
-                int v[8];
-#pragma unroll
-                for (int rr = 0; rr < 8; rr++) v[rr] = db[rr * 8];
-                if (intra_r && col == 0) v[0] = (int)((uint32_t)dc_col << 8);       // b[0] <<= 8, player.cpp:1065
-                idct8<false>(v);
-#pragma unroll
-                for (int rr = 0; rr < 8; rr++) db[rr * 8] = v[rr];
-            }
-            __syncwarp();
-            // row pass: luma lanes own (rblk, rrow); chroma lanes 0..15 own (4 + lane/8, lane%8)
-            const bool ocoded = lane_on && (live >> oblk) & 1;
+        for (int p = 0; p < 3; p++) {
+            const bool luma = p < 2;
+            const int oblk = luma ? 2 * p + phalf : 4 + cplane;
+            const int orow = luma ? prow : crow;
             int w[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) w[i] = 0;
-            if (lane_on) {
+            if (pass_on & (1u << p)) {                                           // warp-uniform
+                const int dc_row = (int)__shfl_sync(0xFFFFFFFFu, recw, hb + 4 + oblk);
                 int4* rowp = (int4*)(dense + oblk * kDenseStride + orow * 8);
                 const int4 a = rowp[0], b = rowp[1];
                 rowp[0] = make_int4(0, 0, 0, 0); rowp[1] = make_int4(0, 0, 0, 0);    // leave the scratch zeroed for the next macroblock
                 w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-            }
-            if (ocoded) {
-                if (!((n1m >> oblk) & 1)) idct8<true>(w);
-                else {                                               // n == 1: dc = b[0] >> 8 (Q5); after the column pass every row holds b[0] in column 0
-                    const int dc = intra_r ? dc_row : w[0] >> 8;
+                if ((live >> oblk) & 1) {
+                    if (!((n1m >> oblk) & 1)) idct8<true>(w);
+                    else {                                           // n == 1: dc = b[0] >> 8 (Q5); after the column pass every row holds b[0] in column 0
+                        const int dc = intra_r ? dc_row : w[0] >> 8;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) w[i] = dc;
+                        for (int i = 0; i < 8; i++) w[i] = dc;
+                    }
                 }
             }
-            if (set == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) resY[i] = w[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) resC[i] = w[i];
+            // prediction: the four cases of mocomp()
+            uint32_t q0 = 0, q1 = 0;
+            if (do_mc) {
+                PredWords pw;
+                if (luma) {
+                    const int lx = (hx >> 1) + phalf * 8, ly = (hy >> 1) + p * 8 + prow;
+                    if (inside) pred_words_staged<true>(stage, 0, lx, ly, tx0, ty0, hy & 1, pw);
+                    else pred_words_clamped<true>(ref, 0, lx, ly, hy & 1, pw);
+                    pred_finish(pw, lx, hx & 1, hy & 1, q0, q1);
+                } else {
+                    const int kx = cx >> 1, ky = (cy >> 1) + crow;
+                    if (inside) pred_words_staged<false>(stage, cplane, kx, ky, tx0, ty0, cy & 1, pw);
+                    else pred_words_clamped<false>(ref, cplane, kx, ky, cy & 1, pw);
+                    pred_finish(pw, kx, cx & 1, cy & 1, q0, q1);
+                }
             }
-            __syncwarp();
-        }
-
-        // ---- finish the prediction, combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
-        uint32_t py0 = 0, py1 = 0, pc0 = 0, pc1 = 0;
-        if (!intra_r) {
-            PredWords wy, wc;
-            if (inside) {
-                mbar_wait(sbar, bar_phase);
-                bar_phase ^= 1;
-                pred_words_staged<true>(stage, 0, lx, ly, tx0, ty0, hy & 1, wy);
-                if (lane < 16) pred_words_staged<false>(stage, cplane, kx, ky, tx0, ty0, cy & 1, wc);
-            } else {
-                pred_words_clamped<true>(ref, 0, lx, ly, hy & 1, wy);
-                if (lane < 16) pred_words_clamped<false>(ref, cplane, kx, ky, cy & 1, wc);
-            }
-            pred_finish(wy, lx, hx & 1, hy & 1, py0, py1);
-            if (lane < 16) pred_finish(wc, kx, cx & 1, cy & 1, pc0, pc1);
-        }
-        {
-            const bool coded = (cbp >> rblk) & 1, aborted = (abm >> rblk) & 1, n1 = (n1m >> rblk) & 1;
-            uint32_t o0 = py0, o1 = py1;
-            bool store = true;
+            // combine + store (copy_block / copy_block_dc / add_block / add_block_dc)
+            const bool coded = (cbp >> oblk) & 1, aborted = (abm >> oblk) & 1, n1 = (n1m >> oblk) & 1;
+            uint32_t o0 = q0, o1 = q1;
+            bool store = valid;
             if (coded && !aborted) {
                 if (intra_r && n1) {                                 // copy_block_dc: replicated, not clamped (Q7)
-                    uint32_t d = (uint32_t)resY[0]; d |= d << 8; d |= d << 16;
+                    uint32_t d = (uint32_t)w[0]; d |= d << 8; d |= d << 16;
                     o0 = o1 = d;
                 } else {
-                    o0 = pin4(py0, resY[0], resY[1], resY[2], resY[3]);
-                    o1 = pin4(py1, resY[4], resY[5], resY[6], resY[7]);
+                    o0 = pin4(q0, w[0], w[1], w[2], w[3]);
+                    o1 = pin4(q1, w[4], w[5], w[6], w[7]);
                 }
             } else if (intra_r) store = false;                        // aborted intra block: destination untouched
-            if (store) *(uint2*)(cur + tile + prow * 16 + phalf * 8) = make_uint2(o0, o1);
+            uint8_t* dst = cur + tile + (luma ? (p * 8 + prow) * 16 + phalf * 8 : 256 + cplane * 64 + crow * 8);
+            if (store) *(uint2*)dst = make_uint2(o0, o1);
         }
-        if (lane < 16) {
-            const int bk = 4 + cplane;
-            const bool coded = (cbp >> bk) & 1, aborted = (abm >> bk) & 1, n1 = (n1m >> bk) & 1;
-            uint32_t o0 = pc0, o1 = pc1;
-            bool store = true;
-            if (coded && !aborted) {
-                if (intra_r && n1) {
-                    uint32_t d = (uint32_t)resC[0]; d |= d << 8; d |= d << 16;
-                    o0 = o1 = d;
-                } else {
-                    o0 = pin4(pc0, resC[0], resC[1], resC[2], resC[3]);
-                    o1 = pin4(pc1, resC[4], resC[5], resC[6], resC[7]);
-                }
-            } else if (intra_r) store = false;
-            if (store) *(uint2*)(cur + tile + 256 + cplane * 64 + crow * 8) = make_uint2(o0, o1);
-        }
-
         __syncwarp();
     }
 }
@@ -773,21 +754,37 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic, int pic_rel)
 // host-side launch helpers -----------------------------------------------------------------------
 size_t ef_recon_smem_bytes() { return (size_t)kReconWarps * kWarpBytes; }
 
+static int g_parse_ctas = kParseCtasPerSm, g_recon_ctas = kReconCtasPerSm;   // resident CTAs per SM, measured by the occupancy API
+
 cudaError_t ef_decode_configure()
 {
-    return cudaFuncSetAttribute(ef_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ef_recon_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(ef_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ef_recon_smem_bytes());
+    if (e != cudaSuccess) return e;
+    // K1b wants shared memory (two macroblock scratch areas per warp), not L1
+    e = cudaFuncSetAttribute(ef_recon_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ef_recon_kernel, kReconWarps * 32, ef_recon_smem_bytes());
+    if (e != cudaSuccess) return e;
+    if (n >= 1) g_recon_ctas = n;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ef_parse_kernel, kParseThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (n >= 1) g_parse_ctas = n;
+    return cudaSuccess;
 }
+
+int ef_decode_resident_ctas(int which) { return which == 0 ? g_parse_ctas : g_recon_ctas; }
 
 // parse every slice of picture indices [pic0, pic0 + n_pics) into record pictures 0 .. n_pics-1
 cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream)
 {
-    ef_parse_kernel<<<sm_count * kParseCtasPerSm, kParseThreads, 0, stream>>>(dev, pic0, n_pics);
+    ef_parse_kernel<<<sm_count * g_parse_ctas, kParseThreads, 0, stream>>>(dev, pic0, n_pics);
     return cudaGetLastError();
 }
 
-// rebuild picture index `pic` of every stream from record picture `pic_rel`
-cudaError_t ef_launch_recon(const EfDev* dev, int pic, int pic_rel, int sm_count, cudaStream_t stream)
+// rebuild one picture index of every stream from record picture `pic_rel`
+cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, cudaStream_t stream)
 {
-    ef_recon_kernel<<<sm_count * kReconCtasPerSm, kReconWarps * 32, ef_recon_smem_bytes(), stream>>>(dev, pic, pic_rel);
+    ef_recon_kernel<<<sm_count * g_recon_ctas, kReconWarps * 32, ef_recon_smem_bytes(), stream>>>(dev, pic_rel);
     return cudaGetLastError();
 }

@@ -1,12 +1,23 @@
 #!/bin/bash
-# tools/sweep_k1.sh — tuning sweep of K1's warps-per-CTA / list-capacity (run on the GPU box via gpurun)
-for cfg in "15 80" "15 64" "16 72" "14 96" "16 64"; do
-  set -- $cfg
-  EF_NVCC_DEFS="-DEF_K1_WARPS=$1 -DEF_K1_LIST=$2" python -c "
-from espflix_b200 import build; s=build.build_cuda(force=True, verbose_ptxas=True)
-import re; print('cfg $1 $2', re.findall(r'ef_decode_kernel.*?Used (\d+) registers', s, re.S)[-1:], [l for l in s.splitlines() if 'spill' in l][-8:-7])"
-  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --streams 4096 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('RESULT $1 $2', round(d['value']), round(d['roofline']['k1_ms_per_step'],2))"
+# tools/sweep_k1.sh — rebuild libespflix_b200.so with different K1 launch shapes and time each on the GPU
+# (run under gpurun; results in gpurun_out/sweep_k1.txt). Usage: tools/sweep_k1.sh "<nvcc defs>" ...
+out=gpurun_out/sweep_k1.txt; : > $out
+for defs in "$@"; do
+  EF_NVCC_DEFS="$defs" python -c "
+from espflix_b200 import build
+build.build_cuda(force=True)" >/dev/null 2>&1
+  EF_VERBOSE=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu > /tmp/sweep.json 2> /tmp/sweep.err
+  python - "$defs" <<'PY' >> $out
+import json, sys
+try:
+    d = json.load(open("/tmp/sweep.json"))
+    print("%-60s value %.0f ms/step %.2f k1 %.2f e2e %.0f" % (sys.argv[1], d["value"], d["ms_per_step"], d["roofline"]["k1_ms_per_step"], d["e2e"]["value"]))
+except Exception as e:
+    print("%-60s FAILED %s" % (sys.argv[1], e))
+PY
+  grep "resident" /tmp/sweep.err | head -1 >> $out
 done
 python -c "
-from espflix_b200 import build; build.build_cuda(force=True)"
+from espflix_b200 import build
+build.build_cuda(force=True)" >/dev/null 2>&1
+cat $out
