@@ -33,13 +33,19 @@
 #define EF_MBH_MAX 12
 #define EF_TILE 384          // bytes per macroblock tile: 256 Y + 64 + 64 chroma
 #ifndef EF_K1A_THREADS
-#define EF_K1A_THREADS 256   // K1a (parse): threads per CTA, CTAs per SM (register bound)
+#define EF_K1A_THREADS 224   // K1a (parse): threads per CTA, CTAs per SM (28 warps per SM with 72 registers measured faster than 32 with 64)
 #endif
 #ifndef EF_K1A_CTAS
 #define EF_K1A_CTAS 4
 #endif
+#ifndef EF_K1A_PF_L1
+#define EF_K1A_PF_L1 0
+#endif
+#ifndef EF_K1A_HDR_BATCH
+#define EF_K1A_HDR_BATCH 32      // 32 = a symbol loop runs until no lane is busy (measured best: header phases are expensive)
+#endif
 #ifndef EF_K1B_WARPS
-#define EF_K1B_WARPS 8       // K1b (reconstruct): warps per CTA, CTAs per SM
+#define EF_K1B_WARPS 7       // K1b (reconstruct): warps per CTA, CTAs per SM
 #endif
 #ifndef EF_K1B_CTAS
 #define EF_K1B_CTAS 4

@@ -38,6 +38,7 @@ namespace {
 
 constexpr int kParseThreads = EF_K1A_THREADS;   // per CTA
 constexpr int kParseCtasPerSm = EF_K1A_CTAS;
+constexpr int kHdrBatch = EF_K1A_HDR_BATCH;        // waiting lanes that end a symbol loop early
 constexpr int kReconWarps = EF_K1B_WARPS;       // per CTA
 constexpr int kReconCtasPerSm = EF_K1B_CTAS;
 
@@ -76,7 +77,12 @@ struct BitReader {
     {
         const uint32_t* a = words + idx;
         const uint32_t v = __ldg(a);
-        if ((idx & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 32));   // 128 bytes ahead of this slice's read position
+        if ((idx & 7) == 0) {                       // once per 32-byte sector
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 32));   // 128 bytes ahead of this slice's read position
+#if EF_K1A_PF_L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 16));   // and the sector after next into L1
+#endif
+        }
         idx++;
         return v;
     }
@@ -166,15 +172,16 @@ __device__ __forceinline__ void idct8(int (&v)[8])
     }
 }
 
-// dequantise one level (block(), player.cpp:1110-1119): v = 2*level (+-1 when not intra);
-// v = (v * qscale * q) / 16 with C truncation; oddify (Q2: 0 becomes +1); clamp to [-2048, 2047].
-__device__ __forceinline__ int dequant(int level, int intra, int qsq)
+// dequantise one level given as magnitude + sign (block(), player.cpp:1110-1119): v = 2*level (+-1 when
+// not intra; +1 for level 0); v = (v * qscale * q) / 16 with C truncation, i.e. on the magnitude; oddify
+// towards zero, except that 0 becomes +1 whatever the sign was (Q2); clamp to [-2048, 2047].
+__device__ __forceinline__ int dequant(int mag, int neg, int intra, int qsq)
 {
-    int v = level << 1;
-    if (!intra) v += v < 0 ? -1 : 1;
-    v = (v * qsq) / 16;
-    if ((v & 1) == 0) v -= v > 0 ? 1 : -1;
-    return max(-2048, min(2047, v));
+    int m = ((2 * mag + (intra ? 0 : 1)) * qsq) >> 4;
+    if (m == 0) neg = 0;
+    m = (max(m, 1) - 1) | 1;
+    m = min(m, 2047 + neg);
+    return neg ? -m : m;
 }
 
 __device__ __forceinline__ uint32_t pin4(uint32_t pred, int r0, int r1, int r2, int r3)
@@ -403,6 +410,11 @@ __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
 
 // =================================================================================================
 // K1a: bitstream -> macroblock records, every slice of pictures [pic0, pic0 + n_pics) in one launch
+//
+// Lane states: no slice (idle / exhausted), WAITING for the header of its next macroblock, BUSY in the
+// coefficient state machine. Header phases (flush finished records, refill idle lanes, parse headers)
+// alternate with symbol loops (one VLC symbol per busy lane per step); a symbol loop ends when no lane is
+// busy or when kHdrBatch lanes are waiting - lanes do not wait for the slowest macroblock of the warp.
 // =================================================================================================
 __global__ void __launch_bounds__(kParseThreads, kParseCtasPerSm)
 ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
@@ -425,126 +437,135 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
     const uint32_t n_slots = (uint32_t)D.n_streams * (EF_MBW_MAX * EF_MBH_MAX);
 
     SliceState s;
-    s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qtab = T.qdef; s.mbw = 0;
-    bool active = false, exhausted = false;
+    s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qtab = T.qdef; s.mbw = 0; s.mb_x = s.mb_y = 0;
+    bool active = false, exhausted = false, busy = false;
+    // the macroblock in flight: info word under construction (bit 0 set = a record is owed), entry count |
+    // skip run << 16, motion vector, record slot
+    uint32_t info_acc = 0, cntw = 0, mvw = 0, slot = 0;
+    int cbp_rem = 0, blk = 0, n = -1, intra = 0;              // n < 0: the next symbol starts a block
     // first round: thread t takes slice t; afterwards lanes whose slice ended pull from the cursor
     const uint32_t first_round = gridDim.x * blockDim.x;
     bool first_fill = true;
 
     for (;;) {
-        // ---- refill idle lanes with new slices -------------------------------------------------
-        unsigned need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
-        if (need) {
-            uint32_t base;
-            if (first_fill) {
-                base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
-                first_fill = false;
-            } else {
-                base = 0;
-                int leader = __ffs(need) - 1;
-                if (lane == leader) base = first_round + atomicAdd(D.parse_cursor, (uint32_t)__popc(need));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            }
-            if (!active && !exhausted) {
-                uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1));
-                if (idx >= total) exhausted = true;
-                else {
-                    const EfWork w = work[idx];
-                    const int code = w.info & 255;
-                    s.ptype = (w.info >> 8) & 7; s.full_pel = (w.info >> 11) & 1; s.r_size = (w.info >> 12) & 7;
-                    const EfSeq* seq = D.seq + (size_t)w.stream * (D.max_seq + 1) + (w.info >> 16);
-                    s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
-                    s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
-                    s.qtab = seq->custom ? (const uint8_t*)seq->q_scan : (const uint8_t*)T.qdef;
-                    const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
-                    s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
-                    s.slot_base |= ((D.base_pics[w.stream] + w.pic + 1u) & 1u) << 31;      // destination frame store: flush_picture(), player.cpp:692
-                    s.wptr = D.coef + 3 * byte_off;          // >= 3 bits of bitstream per coefficient: lists cannot collide
-                    s.br.init(D.es, byte_off);
-                    s.mb_y = code - 2; s.mb_x = s.mbw - 1;   // slice(), player.cpp:1255: the first increment lands on column 0 of row code-1
-                    s.first = 1;
-                    s.dc_y = s.dc_cr = s.dc_cb = 128; s.mv_h = s.mv_v = 0;
-                    active = code >= 1 && code <= s.mbh && s.mbw > 0 && seq->valid;
-                    if (active) {
-                        s.qscale = (int)s.br.get(5);
-                        while (s.br.get(1)) s.br.skip(8);    // extra_information_slice
+        // ---- header phase: records of finished macroblocks ------------------------------------------
+        if (!busy && (info_acc & 1u)) {
+            const uint32_t cnt = cntw & 0xFFFFu;
+            const uint64_t li = (uint64_t)(s.wptr - D.coef) - cnt;
+            *(uint4*)(D.mb_rec + slot) = make_uint4(cntw, mvw, (uint32_t)li, (uint32_t)(li >> 32));
+            D.mb_info[slot] = info_acc | ((uint32_t)s.mbw << 20) | ((s.slot_base >> 31) << 25);
+            info_acc = 0;
+        }
+        // ---- refill lanes without a slice, parse the header of every waiting lane -------------------
+        do {
+            unsigned need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+            if (need) {
+                uint32_t base;
+                if (first_fill) {
+                    base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
+                    first_fill = false;
+                } else {
+                    base = 0;
+                    int leader = __ffs(need) - 1;
+                    if (lane == leader) base = first_round + atomicAdd(D.parse_cursor, (uint32_t)__popc(need));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                }
+                if (!active && !exhausted) {
+                    uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1));
+                    if (idx >= total) exhausted = true;
+                    else {
+                        const EfWork w = work[idx];
+                        const int code = w.info & 255;
+                        s.ptype = (w.info >> 8) & 7; s.full_pel = (w.info >> 11) & 1; s.r_size = (w.info >> 12) & 7;
+                        const EfSeq* seq = D.seq + (size_t)w.stream * (D.max_seq + 1) + (w.info >> 16);
+                        s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
+                        s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
+                        s.qtab = seq->custom ? (const uint8_t*)seq->q_scan : (const uint8_t*)T.qdef;
+                        const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
+                        s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
+                        s.slot_base |= ((D.base_pics[w.stream] + w.pic + 1u) & 1u) << 31;      // destination frame store: flush_picture(), player.cpp:692
+                        s.wptr = D.coef + 3 * byte_off;          // >= 3 bits of bitstream per coefficient: lists cannot collide
+                        s.br.init(D.es, byte_off);
+                        s.mb_y = code - 2; s.mb_x = s.mbw - 1;   // slice(), player.cpp:1255: the first increment lands on column 0 of row code-1
+                        s.first = 1;
+                        s.dc_y = s.dc_cr = s.dc_cb = 128; s.mv_h = s.mv_v = 0;
+                        active = code >= 1 && code <= s.mbh && s.mbw > 0 && seq->valid;
+                        if (active) {
+                            s.qscale = (int)s.br.get(5);
+                            while (s.br.get(1)) s.br.skip(8);    // extra_information_slice
+                        }
                     }
                 }
             }
-        }
-        if (__all_sync(0xFFFFFFFFu, !active)) break;
+            if (active && !busy && !(info_acc & 1u)) {
+                uint32_t skipw = 0;
+                if (parse_header(s, T, cbp_rem, intra, skipw, mvw)) {
+                    slot = (s.slot_base & 0x7FFFFFFFu) + (uint32_t)(s.mb_y * EF_MBW_MAX + s.mb_x);
+                    info_acc = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp_rem << 2);
+                    cntw = skipw << 16;
+                    n = -1;
+                    busy = cbp_rem != 0;
+                } else active = false;
+            }
+        } while (__any_sync(0xFFFFFFFFu, !active && !exhausted));
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
 
-        // ---- every lane parses the header of the next macroblock of its slice -------------------
-        bool have = false;
-        int cbp_rem = 0, intra = 0;
-        uint32_t skipw = 0, mvw = 0;
-        if (active) {
-            have = parse_header(s, T, cbp_rem, intra, skipw, mvw);
-            if (!have) active = false;
-        }
-        const int cbp_all = cbp_rem;
-        const uint32_t slot = (s.slot_base & 0x7FFFFFFFu) + (uint32_t)(s.mb_y * EF_MBW_MAX + s.mb_x);
-        EfMbRec* rec = D.mb_rec + slot;
-        uint32_t* const list0 = s.wptr;
-
-        // ---- flat coefficient state machine, one VLC symbol per lane per step ---------------------
-        int n1mask = 0, abortmask = 0, blk = 0, n = 0;
-        bool busy = have && cbp_rem != 0, start = true;
+        // ---- symbol loop: one VLC symbol per busy lane per step -----------------------------------------
         const uint8_t* qrow = s.qtab + (intra ? 0 : 64);
-        while (__any_sync(0xFFFFFFFFu, busy)) {
+        for (;;) {
+            const unsigned bmask = __ballot_sync(0xFFFFFFFFu, busy);
+            if (!bmask) break;
+            if (__popc(__ballot_sync(0xFFFFFFFFu, active && !busy)) >= kHdrBatch) break;
             if (busy) {
                 BitReader& br = s.br;
-                if (start) {                                   // next coded block of this macroblock
+                if (n < 0) {                                   // next coded block of this macroblock
                     blk = __ffs(cbp_rem) - 1;
                     cbp_rem &= cbp_rem - 1;
                     n = 0;
-                    if (intra) { rec->dc[blk] = parse_dc(s, blk); n = 1; }
-                    start = false;
+                    if (intra) { D.mb_rec[slot].dc[blk] = parse_dc(s, blk); n = 1; }
                 }
                 const uint32_t bits = br.peek();
                 const int lz = min(__clz(bits), 12);               // row 12 / 25 = not a code
                 // index = row * 32 + the five bits after the leading one; (bits << lz) >> 26 is "1xxxxx" = 32 + those bits
                 const int ctx = n == 0 ? 13 * 32 - 32 : -32;       // first-coefficient context lives in rows 13..25
                 const uint32_t e = T.dct[ctx + lz * 32 + (int)((bits << lz) >> 26)];
-                int len = e & 31, run = (e >> 5) & 31, level = (int)(e >> 10);
+                int len = e & 31, run = (e >> 5) & 31, mag = (int)(e >> 10);     // mag = |level|
+                int neg = (int)((bits >> ((32 - len) & 31)) & 1);                      // sign = last bit of a regular code
                 bool end_block = false, derail = false;
-                if (level) {
-                    if ((bits >> (32 - len)) & 1) level = -level;
-                } else if (len == 2) {                         // '10': end of block (player.cpp:1075)
-                    end_block = true;
-                    if (n == 1) n1mask |= 1 << blk;            // Q5
-                } else if (run == 1) {                         // escape: 6-bit run, 8- or 16-bit level (player.cpp:1092)
-                    run = (int)((bits >> 20) & 63);
-                    const int b = (int)((bits >> 12) & 255);
-                    if (b == 0) { level = (int)((bits >> 4) & 255); len = 28; }
-                    else if (b == 128) { level = (int)((bits >> 4) & 255) - 256; len = 28; }
-                    else { level = (int)(int8_t)b; len = 20; }
-                } else derail = true;                          // not a code: the reference derails here
+                if (!mag) {
+                    if (len == 2) {                            // '10': end of block (player.cpp:1075)
+                        end_block = true;
+                        if (n == 1) info_acc |= 0x100u << blk; // Q5
+                    } else if (run == 1) {                     // escape: 6-bit run, 8- or 16-bit level (player.cpp:1092)
+                        run = (int)((bits >> 20) & 63);
+                        const int b = (int)((bits >> 12) & 255);
+                        int level;
+                        if (b == 0) { level = (int)((bits >> 4) & 255); len = 28; }
+                        else if (b == 128) { level = (int)((bits >> 4) & 255) - 256; len = 28; }
+                        else { level = (int)(int8_t)b; len = 20; }
+                        mag = abs(level); neg = level < 0;
+                    } else derail = true;                      // not a code: the reference derails here
+                }
                 if (derail) {                                  // give up on this and the remaining blocks, end the slice
-                    abortmask |= (1 << blk) | cbp_rem;
+                    info_acc |= ((1u << blk) | (uint32_t)cbp_rem) << 14;
                     s.mb_y = s.mbh;
                     busy = false;
                 } else {
                     br.skip(len);
                     if (!end_block) {
                         n += run;
-                        if (n >= 64) { abortmask |= 1 << blk; end_block = true; }      // block() returns -1: nothing is stored
+                        if (n >= 64) { info_acc |= 0x4000u << blk; end_block = true; }     // block() returns -1: nothing is stored
                         else {
-                            const int v = dequant(level, intra, s.qscale * (int)qrow[n]);
+                            const int v = dequant(mag, neg, intra, s.qscale * (int)qrow[n]);
                             const uint32_t zp = T.zp[n];                                   // zz = zig_zag[n]; b[zz] = v * scale_dct_q[zz] (player.cpp:1108, 1121)
                             *s.wptr++ = ((uint32_t)(v * (int)(zp >> 8)) & 0x3FFFFu) | ((zp & 63u) << 18) | ((uint32_t)blk << 24);
+                            cntw++;
                             n++;
                         }
                     }
-                    if (end_block) { start = true; busy = cbp_rem != 0; }
+                    if (end_block) { n = -1; busy = cbp_rem != 0; }
                 }
             }
-        }
-        if (have) {
-            const uint64_t li = (uint64_t)(list0 - D.coef);
-            *(uint4*)rec = make_uint4((uint32_t)(s.wptr - list0) | (skipw << 16), mvw, (uint32_t)li, (uint32_t)(li >> 32));
-            D.mb_info[slot] = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp_all << 2) | ((uint32_t)n1mask << 8) |
-                              ((uint32_t)abortmask << 14) | ((uint32_t)s.mbw << 20) | ((s.slot_base >> 31) << 25);
         }
     }
 }
