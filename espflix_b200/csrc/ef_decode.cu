@@ -62,42 +62,54 @@ struct SharedTables {                           // same layout as the head of Ef
 constexpr int kTableBytes = (sizeof(SharedTables) + 15) & ~15;
 
 // ---------------------------------------------------------------------------------------------
-// bit reader (FILL_BITS/peek_bits/get_bits, player.cpp:348-352, 495-514): MSB-first. `hi` holds
-// the current 32-bit word, `lo` the next one, `nx` the one after (prefetched), pos = bits of `hi`
-// already consumed. peek() is a single funnel shift. Reads run at most 12 bytes past the slice
-// plus the 8 prefetched ones (into the next start code); the ES blob carries 256 bytes of zero padding at its end.
+// bit reader (FILL_BITS/peek_bits/get_bits, player.cpp:348-352, 495-514): MSB-first. `hi` holds the
+// current 32-bit word, `lo` the next one, pos = bits of `hi` already consumed; peek() is a single funnel
+// shift. The words after `lo` come through a per-lane ring of 8 words in shared memory filled by 4-byte
+// cp.async copies issued 7 words ahead: a register scoreboard is warp-wide, so a plain look-ahead load
+// into a register stalls ALL lanes at the next refill of ANY lane (that was 1/3 of K1a's stall samples);
+// the asynchronous copies involve no register. Reads run at most 12 bytes past the slice plus the 28
+// prefetched ones (into the next start code); the ES blob carries 256 bytes of zero padding at its end.
 // ---------------------------------------------------------------------------------------------
+constexpr int kRingStride = kParseThreads * 4;          // bytes between ring slots of one lane: slot-major, conflict-free
+constexpr int kRingBytes = 8 * kRingStride;
+
 struct BitReader {
     const uint32_t* words;   // the whole ES blob as aligned 32-bit words (cudaMalloc alignment)
-    uint32_t idx;            // next word to fetch
-    uint32_t hi, lo, nx_raw, nx2_raw;   // two prefetched words, still little-endian: their loads are not waited for until they are needed
+    uint32_t rp;             // index of the next word to take from the ring
+    uint32_t sring;          // shared-window address of this lane's ring slot 0
+    uint32_t hi, lo;
     int pos;
 
-    __device__ __forceinline__ uint32_t fetch_raw()
+    __device__ __forceinline__ void copy_in(uint32_t widx)
     {
-        const uint32_t* a = words + idx;
-        const uint32_t v = __ldg(a);
-        if ((idx & 7) == 0) {                       // once per 32-byte sector
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 32));   // 128 bytes ahead of this slice's read position
-#if EF_K1A_PF_L1
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 16));   // and the sector after next into L1
-#endif
-        }
-        idx++;
-        return v;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sring + (widx & 7u) * kRingStride), "l"(words + widx) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __device__ __forceinline__ void init(const uint8_t* blob, uint64_t byte_off)
     {
         words = (const uint32_t*)blob;
-        idx = (uint32_t)(byte_off >> 2);
+        const uint32_t w0 = (uint32_t)(byte_off >> 2);
         pos = (int)(byte_off & 3) * 8;
-        hi = __byte_perm(fetch_raw(), 0, 0x0123); lo = __byte_perm(fetch_raw(), 0, 0x0123); nx_raw = fetch_raw(); nx2_raw = fetch_raw();
+        asm volatile("cp.async.wait_all;" ::: "memory");      // copies of the previous slice must not land in the new ring
+        rp = w0 + 2;
+#pragma unroll
+        for (int k = 0; k < 7; k++) copy_in(rp + k);
+        hi = __byte_perm(__ldg(words + w0), 0, 0x0123); lo = __byte_perm(__ldg(words + w0 + 1), 0, 0x0123);
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }
     __device__ __forceinline__ void skip(int n)
     {
         pos += n;
-        if (pos >= 32) { pos -= 32; hi = lo; lo = __byte_perm(nx_raw, 0, 0x0123); nx_raw = nx2_raw; nx2_raw = fetch_raw(); }
+        if (pos >= 32) {
+            pos -= 32; hi = lo;
+            asm volatile("cp.async.wait_group 6;" ::: "memory");          // word rp has landed (7 copies in flight, one group each)
+            uint32_t raw;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(sring + (rp & 7u) * kRingStride) : "memory");
+            lo = __byte_perm(raw, 0, 0x0123);
+            copy_in(rp + 7);                                              // into the slot that was read one refill ago
+            if ((rp & 7u) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + rp + 32));   // 128 bytes ahead of this slice's read position
+            rp++;
+        }
     }
     __device__ __forceinline__ uint32_t get(int n)     // 1 <= n <= 32
     {
@@ -419,7 +431,7 @@ __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
 __global__ void __launch_bounds__(kParseThreads, kParseCtasPerSm)
 ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
 {
-    __shared__ __align__(16) uint8_t smem[kTableBytes];
+    __shared__ __align__(16) uint8_t smem[kTableBytes + kRingBytes];
     SharedTables& T = *(SharedTables*)smem;
     const EfDev& D = *Dp;
     {   // stage the tables (the first sizeof(SharedTables) bytes of EfTables have the same layout)
@@ -438,6 +450,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
 
     SliceState s;
     s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qtab = T.qdef; s.mbw = 0; s.mb_x = s.mb_y = 0;
+    s.br.sring = smem_u32(smem + kTableBytes) + threadIdx.x * 4;
     bool active = false, exhausted = false, busy = false;
     // the macroblock in flight: info word under construction (bit 0 set = a record is owed), entry count |
     // skip run << 16, motion vector, record slot
@@ -515,7 +528,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
         for (;;) {
             const unsigned bmask = __ballot_sync(0xFFFFFFFFu, busy);
             if (!bmask) break;
-            if (__popc(__ballot_sync(0xFFFFFFFFu, active && !busy)) >= kHdrBatch) break;
+            if (kHdrBatch < 32 && __popc(__ballot_sync(0xFFFFFFFFu, active && !busy)) >= kHdrBatch) break;
             if (busy) {
                 BitReader& br = s.br;
                 if (n < 0) {                                   // next coded block of this macroblock
