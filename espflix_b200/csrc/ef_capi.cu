@@ -240,6 +240,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     {   // macroblock records: as many picture indices per K1a launch as fit in 2 GiB
         const size_t per_pic = (size_t)n * EF_MBW_MAX * EF_MBH_MAX * (sizeof(EfMbRec) + 4);
         size_t k = ((size_t)2 << 30) / per_pic;
+        if (const char* e = getenv("EF_REC_PICS")) { const long v = atol(e); if (v >= 1) k = (size_t)v; }   // tuning / test knob
         h.rec_pics = (int)(k < 1 ? 1 : k > (size_t)h.max_pictures ? (size_t)h.max_pictures : k);
         const size_t slots = (size_t)h.rec_pics * n * EF_MBW_MAX * EF_MBH_MAX;
         A(h.mb_info, slots); A(h.mb_rec, slots);

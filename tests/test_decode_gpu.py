@@ -168,3 +168,34 @@ def test_pipelined_submits_and_async_readback(oracle):
         for i, es in enumerate(b):
             assert np.array_equal(outs[k][i], oracle.decode_es(es)[-1]), (k, i)
     ctx.close()
+
+
+@pytest.mark.parametrize("rec_pics", [None, "1", "5"])
+def test_decode_all_multi_picture_parse(oracle, monkeypatch, rec_pics):
+    """ef_decode_all parses every slice of up to rec_pics picture indices in ONE K1a launch and rebuilds
+    them picture by picture; whatever the chunking, the two frame stores of every stream must end up
+    holding its last two pictures. Also: decoding the same index twice gives the same frames."""
+    if rec_pics is None:
+        monkeypatch.delenv("EF_REC_PICS", raising=False)
+    else:
+        monkeypatch.setenv("EF_REC_PICS", rec_pics)
+    streams = [make(i, kw)[0] for i, (_, kw) in enumerate(COVERAGE) if kw["n_pictures"] == 12][:6]
+    streams += [synth.generate(synth.SEED0 + 900 + i)[0] for i in range(11)]
+    streams.append(synth.generate(synth.SEED0 + 950, n_pictures=7)[0])      # a shorter stream in the same batch
+    want = [oracle.decode_es(s) for s in streams]
+    ctx = espflix_b200.Context(n_streams=len(streams), max_pictures=12, es_capacity=sum(len(s) for s in streams) + 4096)
+    blob, off = ctx.pack(streams)
+    ctx.submit_es(blob, off)
+    for _ in range(2):
+        ctx.index()
+        ctx.decode_all(12)
+        for i, w in enumerate(want):
+            n = w.shape[0]
+            got_last = ctx.read_frame_i420(i, -1)
+            assert np.array_equal(got_last, w[n - 1]), "stream %d last picture: %s" % (i, _first_diff(got_last, w[n - 1]))
+            base = ctx.stream_info(i)[1]
+            got_prev = ctx.read_frame_i420(i, (base + n) & 1 ^ 1)
+            assert np.array_equal(got_prev, w[n - 2]), "stream %d previous picture" % i
+        ctx.reset()
+        ctx.submit_es(blob, off)
+    ctx.close()
