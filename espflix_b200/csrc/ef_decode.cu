@@ -122,7 +122,7 @@ struct BitReader {
 // per-lane slice parser state
 struct SliceState {
     BitReader br;
-    uint32_t* wptr;          // next free entry of this slice's coefficient list in HBM
+    uint32_t* wptr;          // coefficient list of the macroblock in flight (HBM); entries are stored at wptr[cnt]
     uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture | destination frame store << 31
     const uint8_t* qtab;     // scan-order quantiser tables [intra 64 | non-intra 64]: the shared-memory defaults or the stream's own in HBM
     int mbw, mbh;
@@ -134,20 +134,24 @@ struct SliceState {
     int mv_h, mv_v;
 };
 
-__device__ __forceinline__ int motion_component(BitReader& br, const uint16_t* mvtab, int m, int r_size, bool& bad)
+// Headers are parsed from a 32-bit WINDOW (w = br.peek(), `used` bits consumed so far) and the bit reader
+// is advanced once per window: every br.skip() site carries the ring-refill code, and the header phase runs
+// with most lanes diverged, so fewer sites is what counts. Window budgets are noted at each use.
+__device__ __forceinline__ int motion_component(uint32_t w, int& used, const uint16_t* mvtab, int m, int r_size, bool& bad)
 {
-    // motion_vector(), player.cpp:891
-    uint32_t bits = br.peek();
+    // motion_vector(), player.cpp:891; at most 11 + 6 bits
+    const uint32_t bits = w << used;
     int lz = __clz(bits);
     if (lz > 6) { bad = true; return m; }
     uint32_t e = mvtab[lz * 32 + ((bits << (lz + 1)) >> 27)];
     int len = e & 15;
     if (!len) { bad = true; return m; }
     int code = (int)(e >> 4) - 16;
-    br.skip(len);
+    used += len;
     int d = code;
     if (code != 0 && r_size != 0) {
-        d = ((abs(code) - 1) << r_size) + (int)br.get(r_size) + 1;
+        d = ((abs(code) - 1) << r_size) + (int)((w << used) >> (32 - r_size)) + 1;
+        used += r_size;
         if (code < 0) d = -d;
     }
     int scale = 1 << r_size;
@@ -329,18 +333,23 @@ __device__ __forceinline__ bool parse_header(SliceState& s, const SharedTables& 
     uint32_t bits = br.peek();
     if ((bits >> 9) == 0) return false;             // slice_done(): next 23 bits are zero (player.cpp:1238)
 
-    int increment = 0;                              // macroblock_address_increment (player.cpp:1267-1275)
+    // window A: address increment (<= 11 bits) + macroblock_type (<= 6) + quantiser_scale (5)
+    int increment = 0, used;                        // macroblock_address_increment (player.cpp:1267-1275)
+    uint32_t w;
     for (;;) {
-        bits = br.peek();
-        int lz = __clz(bits);
+        w = br.peek();
+        int lz = __clz(w);
         if (lz > 7) return false;
-        uint32_t e = T.mba[lz * 32 + ((bits << (lz + 1)) >> 27)];
+        uint32_t e = T.mba[lz * 32 + ((w << (lz + 1)) >> 27)];
         int len = e & 15, val = (int)(e >> 4);
         if (!len) return false;
-        br.skip(len);
-        if (val == 34) continue;                    // stuffing
-        if (val == 35) { increment += 33; continue; }   // escape
+        if (val >= 34) {                            // 34 stuffing, 35 escape: consume and look again
+            br.skip(len);
+            if (val == 35) increment += 33;
+            continue;
+        }
         increment += val;
+        used = len;
         break;
     }
     int skip_before = 0;
@@ -351,27 +360,34 @@ __device__ __forceinline__ bool parse_header(SliceState& s, const SharedTables& 
     if (s.mb_y >= s.mbh) return false;              // the reference would write past the frame here
 
     int mb_type;                                    // macroblock_type (player.cpp:1292)
-    bits = br.peek();
+    bits = w << used;
     if (s.ptype == 1) {
-        if (bits >> 31) { mb_type = 0x01; br.skip(1); }
-        else if (bits >> 30) { mb_type = 0x11; br.skip(2); }
+        if (bits >> 31) { mb_type = 0x01; used += 1; }
+        else if (bits >> 30) { mb_type = 0x11; used += 2; }
         else return false;
     } else {
         uint32_t e = T.ptype[bits >> 26];
         if (!(e & 7)) return false;
         mb_type = (int)(e >> 3);
-        br.skip(e & 7);
+        used += e & 7;
     }
     const int intra = mb_type & 1;
-    if (mb_type & 0x10) s.qscale = (int)br.get(5);
+    if (mb_type & 0x10) { s.qscale = (int)((w << used) >> 27); used += 5; }
+    br.skip(used);                                  // <= 22 bits
+
     int mvh = 0, mvv = 0;
+    used = 0;
     if (intra) { s.mv_h = s.mv_v = 0; }
     else {
         s.dc_y = s.dc_cr = s.dc_cb = 128;
         if (mb_type & 0x08) {
             bool bad = false;
-            s.mv_h = motion_component(br, T.mv, s.mv_h, s.r_size, bad);
-            s.mv_v = motion_component(br, T.mv, s.mv_v, s.r_size, bad);
+            w = br.peek();                          // window B: horizontal component (<= 17 bits)
+            s.mv_h = motion_component(w, used, T.mv, s.mv_h, s.r_size, bad);
+            br.skip(used);
+            used = 0;
+            w = br.peek();                          // window C: vertical component (<= 17) + coded_block_pattern (<= 9)
+            s.mv_v = motion_component(w, used, T.mv, s.mv_v, s.r_size, bad);
             if (bad) return false;
         } else s.mv_h = s.mv_v = 0;
         mvh = s.mv_h << s.full_pel;                 // predict(), player.cpp:878
@@ -379,12 +395,13 @@ __device__ __forceinline__ bool parse_header(SliceState& s, const SharedTables& 
     }
     int cbp = intra ? 63 : 0;
     if (mb_type & 0x02) {
-        bits = br.peek();
-        uint32_t e = T.cbp[bits >> 23];
+        if (!used) w = br.peek();
+        uint32_t e = T.cbp[(w << used) >> 23];
         if (!(e & 15)) return false;
         cbp = (int)(e >> 4);
-        br.skip(e & 15);
+        used += e & 15;
     }
+    if (used) br.skip(used);
     cbp_out = (int)(__brev((unsigned)cbp) >> 26);   // bit b = block b (the VLC value has block 0 in bit 5)
     intra_out = intra;
     skip_out = (uint32_t)skip_before;
@@ -396,7 +413,7 @@ __device__ __forceinline__ bool parse_header(SliceState& s, const SharedTables& 
 __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
 {
     BitReader& br = s.br;
-    const uint32_t bits = br.peek();
+    const uint32_t bits = br.peek();                // one window: size code (<= 10 bits) + differential (<= 11)
     int dc_size, used, dc;
     if (blk < 4) {
         dc = s.dc_y;
@@ -408,13 +425,13 @@ __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
         if (!(bits >> 31)) { dc_size = (int)((bits >> 30) & 1); used = 2; }
         else { int ones = min(10, __clz(~bits)); dc_size = ones + 1; used = min(dc_size, 10); }
     }
-    br.skip(used);
     if (dc_size) {
-        int delta = (int)br.get(dc_size);
+        int delta = (int)((bits << used) >> (32 - dc_size));
         if (delta & (1 << (dc_size - 1))) dc += delta;
         else dc += (int)((0xFFFFFFFFu << dc_size) | (uint32_t)(delta + 1));
         if (blk < 4) s.dc_y = dc; else if (blk == 4) s.dc_cr = dc; else s.dc_cb = dc;
     }
+    br.skip(used + dc_size);
     return dc;
 }
 
@@ -454,8 +471,9 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
     bool active = false, exhausted = false, busy = false;
     // the macroblock in flight: info word under construction (bit 0 set = a record is owed), entry count |
     // skip run << 16, motion vector, record slot
-    uint32_t info_acc = 0, cntw = 0, mvw = 0, slot = 0;
-    int cbp_rem = 0, blk = 0, n = -1, intra = 0;              // n < 0: the next symbol starts a block
+    uint32_t info_acc = 0, cnt = 0, skipw = 0, mvw = 0, slot = 0;
+    uint32_t blk24 = 0, blkbit = 0;                           // current block: number << 24, 0x100 << number
+    int cbp_rem = 0, n = -1, intra = 0;                       // n < 0: the next symbol starts a block
     // first round: thread t takes slice t; afterwards lanes whose slice ended pull from the cursor
     const uint32_t first_round = gridDim.x * blockDim.x;
     bool first_fill = true;
@@ -463,9 +481,9 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
     for (;;) {
         // ---- header phase: records of finished macroblocks ------------------------------------------
         if (!busy && (info_acc & 1u)) {
-            const uint32_t cnt = cntw & 0xFFFFu;
-            const uint64_t li = (uint64_t)(s.wptr - D.coef) - cnt;
-            *(uint4*)(D.mb_rec + slot) = make_uint4(cntw, mvw, (uint32_t)li, (uint32_t)(li >> 32));
+            const uint64_t li = (uint64_t)(s.wptr - D.coef);
+            *(uint4*)(D.mb_rec + slot) = make_uint4(cnt | (skipw << 16), mvw, (uint32_t)li, (uint32_t)(li >> 32));
+            s.wptr += cnt;
             D.mb_info[slot] = info_acc | ((uint32_t)s.mbw << 20) | ((s.slot_base >> 31) << 25);
             info_acc = 0;
         }
@@ -511,11 +529,10 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                 }
             }
             if (active && !busy && !(info_acc & 1u)) {
-                uint32_t skipw = 0;
                 if (parse_header(s, T, cbp_rem, intra, skipw, mvw)) {
                     slot = (s.slot_base & 0x7FFFFFFFu) + (uint32_t)(s.mb_y * EF_MBW_MAX + s.mb_x);
                     info_acc = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp_rem << 2);
-                    cntw = skipw << 16;
+                    cnt = 0;
                     n = -1;
                     busy = cbp_rem != 0;
                 } else active = false;
@@ -532,7 +549,8 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
             if (busy) {
                 BitReader& br = s.br;
                 if (n < 0) {                                   // next coded block of this macroblock
-                    blk = __ffs(cbp_rem) - 1;
+                    const int blk = __ffs(cbp_rem) - 1;
+                    blk24 = (uint32_t)blk << 24; blkbit = 0x100u << blk;
                     cbp_rem &= cbp_rem - 1;
                     n = 0;
                     if (intra) { D.mb_rec[slot].dc[blk] = parse_dc(s, blk); n = 1; }
@@ -548,7 +566,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                 if (!mag) {
                     if (len == 2) {                            // '10': end of block (player.cpp:1075)
                         end_block = true;
-                        if (n == 1) info_acc |= 0x100u << blk; // Q5
+                        if (n == 1) info_acc |= blkbit;        // Q5
                     } else if (run == 1) {                     // escape: 6-bit run, 8- or 16-bit level (player.cpp:1092)
                         run = (int)((bits >> 20) & 63);
                         const int b = (int)((bits >> 12) & 255);
@@ -560,19 +578,18 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                     } else derail = true;                      // not a code: the reference derails here
                 }
                 if (derail) {                                  // give up on this and the remaining blocks, end the slice
-                    info_acc |= ((1u << blk) | (uint32_t)cbp_rem) << 14;
+                    info_acc |= (blkbit << 6) | ((uint32_t)cbp_rem << 14);
                     s.mb_y = s.mbh;
                     busy = false;
                 } else {
                     br.skip(len);
                     if (!end_block) {
                         n += run;
-                        if (n >= 64) { info_acc |= 0x4000u << blk; end_block = true; }     // block() returns -1: nothing is stored
+                        if (n >= 64) { info_acc |= blkbit << 6; end_block = true; }     // block() returns -1: nothing is stored
                         else {
                             const int v = dequant(mag, neg, intra, s.qscale * (int)qrow[n]);
                             const uint32_t zp = T.zp[n];                                   // zz = zig_zag[n]; b[zz] = v * scale_dct_q[zz] (player.cpp:1108, 1121)
-                            *s.wptr++ = ((uint32_t)(v * (int)(zp >> 8)) & 0x3FFFFu) | ((zp & 63u) << 18) | ((uint32_t)blk << 24);
-                            cntw++;
+                            s.wptr[cnt++] = ((uint32_t)(v * (int)(zp >> 8)) & 0x3FFFFu) | ((zp & 63u) << 18) | blk24;
                             n++;
                         }
                     }
