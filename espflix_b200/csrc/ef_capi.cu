@@ -52,20 +52,21 @@ int fail(int code, const char* fmt, ...)
 
 // device frame stores are macroblock-tiled (ef_common.cuh); these kernels convert to/from the two
 // host-visible layouts: the I420 dump and the reference's strips (video.h:36-44; player.cpp:33-46).
-// mode 0 = I420, 1 = strips. One thread per 4 bytes (4 consecutive pixels never straddle a tile row).
+// mode 0 = I420, 1 = strips. One thread per 8 bytes (8 aligned consecutive bytes never straddle a tile row:
+// luma tile rows are 16 bytes, chroma tile rows 8, and 352, 176 and 528 are multiples of 8).
 __global__ void ef_export_frames_kernel(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ base_pics,
                                         const uint32_t* __restrict__ n_pics, int first, int count, int fb_sel, int mode, uint8_t* __restrict__ dst)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t per = EF_FRAME / 4;
+    const uint32_t per = EF_FRAME / 8;
     const uint32_t k = (uint32_t)(t / per), w = (uint32_t)(t % per);
     if (k >= (uint32_t)count) return;
     const int s = first + (int)k;
     const int fb = fb_sel >= 0 ? fb_sel : (int)((base_pics[s] + n_pics[s]) & 1u);
     const uint8_t* f = frames + ef_frame_offset(s, fb);
-    const int b = (int)w * 4;
+    const int b = (int)w * 8;
     const int src = mode == 0 ? ef_i420_to_tiled(b) : ef_strips_to_tiled(b);
-    *(uint32_t*)(dst + (size_t)k * EF_FRAME + b) = *(const uint32_t*)(f + src);
+    *(uint2*)(dst + (size_t)k * EF_FRAME + b) = *(const uint2*)(f + src);
 }
 
 __global__ void ef_import_frame_kernel(uint8_t* __restrict__ frame, const uint8_t* __restrict__ src, int mode)
@@ -467,7 +468,7 @@ int ef_read_frame(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
     if (rc != EF_OK) return rc;
     rc = ensure_stage(c, EF_FRAME);
     if (rc != EF_OK) return rc;
-    ef_export_frames_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, 1, c->d_stage);
+    ef_export_frames_kernel<<<(EF_FRAME / 8 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, 1, c->d_stage);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaMemcpy(dst, c->d_stage, EF_FRAME, cudaMemcpyDeviceToHost));
@@ -489,7 +490,7 @@ int ef_read_latest_i420_async(ef_ctx* c, int first, int count, uint8_t* dst, voi
     }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaStreamWaitEvent(st, c->ev_down_done[k], 0));        // the previous copy out of this staging buffer has finished
-    const uint64_t threads = (uint64_t)count * (EF_FRAME / 4);
+    const uint64_t threads = (uint64_t)count * (EF_FRAME / 8);
     ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, 0, c->d_stage2[k]);
     CK(cudaGetLastError());
     c->launches++;
@@ -525,7 +526,7 @@ int ef_read_frame_i420(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
     if (rc != EF_OK) return rc;
     rc = ensure_stage(c, EF_FRAME);
     if (rc != EF_OK) return rc;
-    ef_export_frames_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, 0, c->d_stage);
+    ef_export_frames_kernel<<<(EF_FRAME / 8 + 255) / 256, 256>>>(c->h.frames, c->h.base_pics, c->h.n_pics, stream_index, 1, f, 0, c->d_stage);
     CK(cudaGetLastError());
     c->launches++;
     CK(cudaMemcpy(dst, c->d_stage, EF_FRAME, cudaMemcpyDeviceToHost));

@@ -182,10 +182,7 @@ __device__ __forceinline__ void idct8(int (&v)[8])
     int y7 = -x0 - ((b4 * 473 + b6 * 196 + 128) >> 8);
     v[0] = b7 + y4; v[1] = x4 + y3; v[2] = y5 - x0; v[3] = y6 - y7;
     v[4] = y6 + y7; v[5] = x0 + y5; v[6] = y3 - x4; v[7] = y4 - b7;
-    if (kFinal) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] >>= 8;
-    }
+    // kFinal: the outputs are left scaled by 256 (the reference's final >> 8 is folded into pin4)
 }
 
 // dequantise one level given as magnitude + sign (block(), player.cpp:1110-1119): v = 2*level (+-1 when
@@ -202,14 +199,15 @@ __device__ __forceinline__ int dequant(int mag, int neg, int intra, int qsq)
 
 __device__ __forceinline__ uint32_t pin4(uint32_t pred, int r0, int r1, int r2, int r3)
 {
-    // PIN(b + s) for four pixels (add_block, player.cpp:1189; _pin clamps to [0,248], Q1):
-    // max(min(pred + res, 248), 0) is one DPX instruction per pixel. (The packed s16x2 form would
-    // halve this but its 16-bit add could wrap for residuals beyond +-32,512; kept exact for any int.)
-    const int p0 = __viaddmin_s32_relu((int)(pred & 0xFF), r0, 248);
-    const int p1 = __viaddmin_s32_relu((int)((pred >> 8) & 0xFF), r1, 248);
-    const int p2 = __viaddmin_s32_relu((int)((pred >> 16) & 0xFF), r2, 248);
-    const int p3 = __viaddmin_s32_relu((int)(pred >> 24), r3, 248);
-    return __byte_perm(__byte_perm(p0, p1, 0x0040), __byte_perm(p2, p3, 0x0040), 0x5410);
+    // PIN(b + (s >> 8)) for four pixels (add_block, player.cpp:1189; _pin clamps to [0,248], Q1), with the
+    // residuals r still scaled by 256: t = max(min(pred * 256 + r, 248 * 256 + 255), 0) is one DPX instruction
+    // and floor(t / 256) = its byte 1 = clamp(pred + floor(r / 256)) exactly, for any 32-bit r in the IDCT's
+    // range. One PRMT puts a prediction byte into byte 1, three more gather the four result bytes.
+    const int p0 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4404), r0, 0xF8FF);
+    const int p1 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4414), r1, 0xF8FF);
+    const int p2 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4424), r2, 0xF8FF);
+    const int p3 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4434), r3, 0xF8FF);
+    return __byte_perm(__byte_perm(p0, p1, 0x0051), __byte_perm(p2, p3, 0x0051), 0x5410);
 }
 
 // (a+b+1)>>1 on four packed bytes (mocomp cases 1 and 2, player.cpp:777-805)
@@ -748,7 +746,7 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
             const bool luma = p < 2;
             const int oblk = luma ? 2 * p + phalf : 4 + cplane;
             const int orow = luma ? prow : crow;
-            int w[8];
+            int w[8], dcv = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) w[i] = 0;
             if (pass_on & (1u << p)) {                                           // warp-uniform
@@ -758,11 +756,11 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
                 rowp[0] = make_int4(0, 0, 0, 0); rowp[1] = make_int4(0, 0, 0, 0);    // leave the scratch zeroed for the next macroblock
                 w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
                 if ((live >> oblk) & 1) {
-                    if (!((n1m >> oblk) & 1)) idct8<true>(w);
+                    if (!((n1m >> oblk) & 1)) idct8<true>(w);        // residuals scaled by 256
                     else {                                           // n == 1: dc = b[0] >> 8 (Q5); after the column pass every row holds b[0] in column 0
-                        const int dc = intra_r ? dc_row : w[0] >> 8;
+                        dcv = intra_r ? dc_row : w[0] >> 8;
 #pragma unroll
-                        for (int i = 0; i < 8; i++) w[i] = dc;
+                        for (int i = 0; i < 8; i++) w[i] = dcv * 256;
                     }
                 }
             }
@@ -788,7 +786,7 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
             bool store = valid;
             if (coded && !aborted) {
                 if (intra_r && n1) {                                 // copy_block_dc: replicated, not clamped (Q7)
-                    uint32_t d = (uint32_t)w[0]; d |= d << 8; d |= d << 16;
+                    uint32_t d = (uint32_t)dcv; d |= d << 8; d |= d << 16;
                     o0 = o1 = d;
                 } else {
                     o0 = pin4(q0, w[0], w[1], w[2], w[3]);

@@ -72,12 +72,21 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
     uint32_t fp_rs = 0;                                   // full_pel | r_size << 1 of the last P header (stale state a B/D picture would see)
     bool stop = false;
 
-    for (uint64_t chunk = 0; chunk < span && !stop; chunk += 512) {
+    // the sweep is latency bound (one warp per stream): keep the loads of the next two 512-byte chunks in flight
+    auto load_chunk = [&](uint64_t chunk, uint4& v, uint32_t& nxt) {
         const uint64_t o = chunk + (uint64_t)lane * 16;
-        uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        uint32_t nxt = 0xFFFFFFFFu;
+        v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        nxt = 0xFFFFFFFFu;
         if (o < span) v = __ldg((const uint4*)(abase + o));
         if (o + 16 < span) nxt = __ldg((const uint32_t*)(abase + o + 16));
+    };
+    uint4 v, v1, v2;
+    uint32_t nxt, nxt1, nxt2;
+    load_chunk(0, v, nxt);
+    load_chunk(512, v1, nxt1);
+    for (uint64_t chunk = 0; chunk < span && !stop; chunk += 512, v = v1, nxt = nxt1, v1 = v2, nxt1 = nxt2) {
+        const uint64_t o = chunk + (uint64_t)lane * 16;
+        load_chunk(chunk + 1024, v2, nxt2);
         const uint32_t w[5] = { v.x, v.y, v.z, v.w, nxt };
         uint32_t hits = 0;
 #pragma unroll
