@@ -4,13 +4,13 @@
 Workload (BASELINE.json configs[3], SURVEY.md 8d "Config 4"): 4,096 independent synthetic streams
 per GPU, each one GOP of 12 pictures (1 I + 11 P, 12 slices/picture, ~7.4 KB/picture), D=64 distinct
 seeds replicated 64x (replication only bounds generation time; parity of the distinct streams is
-checked in tests/). A step = one pass of the hot path over the batch: K1a index + 12 launches of the
-fused macroblock kernel K1 = 49,152 decoded pictures per GPU.
+checked in tests/). A step = one pass of the hot path over the batch: K0 index + K1a (one parse launch over
+all 589,824 slices) + 12 launches of K1b (reconstruction, one per picture index) = 49,152 decoded pictures per GPU.
 
   value   whole-job frames/s with the elementary streams already resident in HBM (CUDA events, max over ranks)
   e2e     same metric through the C-ABI with HOST buffers: pinned ES -> H2D -> index -> decode -> D2H of the
           last picture of every stream, all inside the timed region
-  roofline  K1: algorithmic bytes (ES + frame written + reference frame read) / summed K1 launch time
+  roofline  K1 (= K1a + K1b): algorithmic bytes (ES + frame written + reference frame read) / time of the pair
   cpu_baseline / --impl reference   the UNMODIFIED reference decoder (oracle/_ref/efref_decode, one process per
           core, Q11) on the box's host cores; falls back to the C restatement (kind "port") if _ref is absent
 Multi-GPU: independent streams shard one batch per rank (weak scaling), no data-path collective; one

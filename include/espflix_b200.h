@@ -87,16 +87,18 @@ int ef_submit_es_device(ef_ctx* ctx, const uint8_t* es, const uint64_t* off, voi
 int ef_submit_ts_host(ef_ctx* ctx, const uint8_t* ts, const uint64_t* off, void* stream);
 int ef_submit_ts_device(ef_ctx* ctx, const uint8_t* ts, const uint64_t* off, void* stream);
 
-/* K1a: start-code scan, header parse, per-picture slice work lists (device side, asynchronous). */
+/* K0: start-code scan, header parse, per-picture slice work lists (device side, asynchronous). */
 int ef_index(ef_ctx* ctx, void* stream);
 /* Synchronising query of the last ef_index: max pictures in any stream, total pictures, total slices. */
 int ef_index_info(ef_ctx* ctx, int* max_pictures, uint64_t* total_pictures, uint64_t* total_slices, uint64_t* es_bytes);
 /* Per-stream picture count of the last submit and pictures decoded before it (host arrays, may be NULL). */
 int ef_stream_info(ef_ctx* ctx, int stream_index, int* n_pictures, int* base_pictures);
 
-/* K1: decode picture #pic (0-based within the submit) of every stream — one launch. */
+/* K1: decode picture #pic (0-based within the submit) of every stream: one parse launch (K1a, bitstream ->
+ * macroblock records) + one reconstruction launch (K1b). */
 int ef_decode_picture(ef_ctx* ctx, int pic, void* stream);
-/* All pictures 0..n_pictures-1 of the submit, back to back on `stream`. */
+/* All pictures 0..n_pictures-1 of the submit on `stream`: K1a parses every slice of all of them in ONE launch
+ * (parsing needs no pixels), then K1b runs once per picture index. Prefer this over a loop of ef_decode_picture. */
 int ef_decode_all(ef_ctx* ctx, int n_pictures, void* stream);
 
 /* Frame stores. fb = 0/1 is the reference's _fb[] index; -1 = the frame holding the most recently
