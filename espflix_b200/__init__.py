@@ -2,6 +2,6 @@
 352x192 I+P streams into the reference's striped YUV frame store, and NTSC/PAL composite field
 synthesis. The product is libespflix_b200.so (C-ABI in include/espflix_b200.h); this package is
 the thin ctypes host layer the tests and bench.py use."""
-from .capi import Context, EspflixError, lib_path, load_library  # noqa: F401
+from .capi import Context, EspflixError, build_video_idx, lib_path, load_library, tsidx_samples, tsidx_scan  # noqa: F401
 
-__all__ = ["Context", "EspflixError", "lib_path", "load_library"]
+__all__ = ["Context", "EspflixError", "lib_path", "load_library", "tsidx_scan", "tsidx_samples", "build_video_idx"]

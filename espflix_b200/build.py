@@ -11,11 +11,12 @@ LIB = os.path.join(PKG, "libespflix_b200.so")
 SYNTH_LIB = os.path.join(PKG, "synth", "libefsynth.so")
 HOST_LIB = os.path.join(PKG, "host", "libespflix_host.so")
 HOST_CLI = os.path.join(PKG, "host", "ef_player_cli")
+INDEXER_CLI = os.path.join(PKG, "host", "ef_indexer_cli")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libef_oracle.so")
 REF_DECODE = os.path.join(ROOT, "oracle", "_ref", "efref_decode")
 REF_VIDEO = os.path.join(ROOT, "oracle", "_ref", "libefref_vid.so")
 
-CUDA_SOURCES = ["ef_capi.cu", "ef_decode.cu", "ef_index.cu", "ef_composite.cu", "ef_tables.cpp"]
+CUDA_SOURCES = ["ef_capi.cu", "ef_decode.cu", "ef_index.cu", "ef_composite.cu", "ef_tsindex.cu", "ef_tables.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -57,7 +58,7 @@ def build_synth(force=False):
 
 def build_host(force=False):
     hdir = os.path.join(PKG, "host")
-    srcs = [os.path.join(hdir, f) for f in ("player_gpu.cpp", "video_gpu.cpp")]
+    srcs = [os.path.join(hdir, f) for f in ("player_gpu.cpp", "video_gpu.cpp", "indexer_gpu.cpp")]
     if not all(os.path.exists(s) for s in srcs):
         return
     deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")]
@@ -66,6 +67,7 @@ def build_host(force=False):
         link = ["-L", PKG, "-lespflix_b200", "-lpthread"]
         _run(["g++"] + common + ["-shared", "-o", HOST_LIB] + srcs + link + ["-Wl,-rpath,$ORIGIN/.."])
         _run(["g++"] + common + ["-o", HOST_CLI, os.path.join(hdir, "ef_player_cli.cpp")] + srcs + link + ["-Wl,-rpath,$ORIGIN/.."])
+        _run(["g++"] + common + ["-o", INDEXER_CLI, os.path.join(hdir, "ef_indexer_cli.cpp")] + srcs + link + ["-Wl,-rpath,$ORIGIN/.."])
 
 
 def build_oracle(force=False):

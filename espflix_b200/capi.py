@@ -61,6 +61,8 @@ _SIGNATURES = {
     "ef_video_isr": (_I, [_VP, _I, _I, _VP]),
     "ef_blit": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I]),
     "ef_launch_count": (ctypes.c_uint64, [_VP]),
+    "ef_tsidx_scan": (_I, [_I, _VP, _VP, _I, ctypes.c_uint32, _VP, _VP, _VP]),
+    "ef_tsidx_samples": (_I, [_I, _VP, _VP, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, _VP, ctypes.c_uint32, _VP]),
 }
 
 
@@ -247,3 +249,62 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.ef_launch_count(self._h))
+
+
+# -- trick-mode index (indexer/indexer.cpp) ---------------------------------------------
+IDX_BIN = 90000 // 12            # merge_index(): one sample per 1/12 s
+_TSIDX_INFO = np.dtype([("first_pts", "<i8"), ("last_pts", "<i8"), ("n_seq", "<u4"), ("n_samples", "<u4")])
+
+
+def _check_rc(lib, rc):
+    if rc != 0:
+        raise EspflixError(rc, lib.ef_last_error().decode("utf-8", "replace"))
+
+
+def tsidx_scan(files, bin_size=IDX_BIN, device=0):
+    """make_index() for a list of transport streams (bytes-like, lengths multiples of 188). Returns one dict per
+    file: first_pts, last_pts, seq_pts (int64 array), seq_pos (uint32 array), n_samples."""
+    lib = load_library()
+    blob, off = Context.pack(files)
+    n_packets = int(off[-1]) // 188
+    info = np.zeros(len(files), dtype=_TSIDX_INFO)
+    spts = np.zeros(max(n_packets, 1), dtype=np.int64)
+    spos = np.zeros(max(n_packets, 1), dtype=np.uint32)
+    blob = np.ascontiguousarray(blob)
+    _check_rc(lib, lib.ef_tsidx_scan(device, blob.ctypes.data if blob.size else spts.ctypes.data, off.ctypes.data, len(files), bin_size,
+                                     info.ctypes.data, spts.ctypes.data, spos.ctypes.data))
+    out = []
+    for f in range(len(files)):
+        p0, n = int(off[f]) // 188, int(info[f]["n_seq"])
+        out.append({"first_pts": int(info[f]["first_pts"]), "last_pts": int(info[f]["last_pts"]), "n_samples": int(info[f]["n_samples"]),
+                    "seq_pts": spts[p0:p0 + n].copy(), "seq_pos": spos[p0:p0 + n].copy()})
+    return out
+
+
+def tsidx_samples(seq_pts, seq_pos, first_pts, last_pts, bin_size=IDX_BIN, device=0):
+    """pts2seq(): uint32 packet number per bin."""
+    lib = load_library()
+    seq_pts = np.ascontiguousarray(seq_pts, dtype=np.int64)
+    seq_pos = np.ascontiguousarray(seq_pos, dtype=np.uint32)
+    n = ctypes.c_uint32(0)
+    cap = 0 if len(seq_pts) == 0 or last_pts < first_pts else (last_pts - first_pts) // bin_size + 1
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    _check_rc(lib, lib.ef_tsidx_samples(device, seq_pts.ctypes.data, seq_pos.ctypes.data, len(seq_pts), first_pts, last_pts, bin_size,
+                                        out.ctypes.data, cap, ctypes.byref(n)))
+    return out[:n.value].copy()
+
+
+def build_video_idx(video_ts, fwd_ts, rev_ts, device=0):
+    """merge_index(): the video.idx image (header + three sample arrays) for main / fast-forward / rewind
+    streams; struct padding is zero (the reference leaves it indeterminate)."""
+    recs = tsidx_scan([video_ts, fwd_ts, rev_ts], IDX_BIN, device)
+    hdr = bytearray(104)
+    hdr[0:8] = np.array([ord("I") | (ord("D") << 8) | (ord("X") << 16), 3], dtype="<u4").tobytes()
+    body = b""
+    for k, r in enumerate(recs):
+        smp = tsidx_samples(r["seq_pts"], r["seq_pos"], r["first_pts"], r["last_pts"], IDX_BIN, device)
+        o = 8 + 32 * k
+        hdr[o:o + 16] = np.array([r["first_pts"], r["last_pts"]], dtype="<i8").tobytes()
+        hdr[o + 16:o + 28] = np.array([IDX_BIN, 1 if k == 0 else 15, len(smp)], dtype="<u4").tobytes()
+        body += smp.astype("<u4").tobytes()
+    return bytes(hdr) + body

@@ -26,6 +26,9 @@ __global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint6
 size_t ef_recon_smem_bytes();
 cudaError_t ef_decode_configure();
 int ef_decode_resident_ctas(int which);
+__global__ void ef_tsidx_packet_kernel(const uint8_t* ts, const uint64_t* pkt_off, int n_files, uint64_t n_packets, int64_t* pkt_pts, uint8_t* pkt_kind);
+__global__ void ef_tsidx_compact_kernel(const uint64_t* pkt_off, const int64_t* pkt_pts, const uint8_t* pkt_kind, int64_t* seq_pts, uint32_t* seq_pos, int64_t* info);
+__global__ void ef_tsidx_sample_kernel(const int64_t* seq_pts, const uint32_t* seq_pos, int n, int64_t first_pts, uint32_t bin_size, uint32_t n_samples, uint32_t* samples);
 cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream);
 cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, cudaStream_t stream);
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream);
@@ -672,5 +675,78 @@ int ef_blit(ef_ctx* c, int stream_index, int fb, uint16_t* dst, int line, int x,
 }
 
 uint64_t ef_launch_count(ef_ctx* c) { return c ? c->launches : 0; }
+
+// ---- trick-mode index (indexer/indexer.cpp), stateless --------------------------------------------------
+namespace {
+struct DevBuf {                      // scoped device allocation
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+};
+uint32_t tsidx_sample_count(uint32_t n_seq, int64_t first, int64_t last, uint32_t bin)
+{
+    if (!n_seq || !bin || last < first) return 0;
+    return (uint32_t)((last - first) / bin + 1);
+}
+}  // namespace
+
+int ef_tsidx_scan(int device, const uint8_t* ts, const uint64_t* off, int n_files, uint32_t bin_size,
+                  ef_tsidx_info* info, int64_t* seq_pts, uint32_t* seq_pos)
+{
+    if (!ts || !off || !info || !seq_pts || !seq_pos || n_files < 1) return fail(EF_EINVAL, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= device) return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", device, cudaGetErrorString(e));
+    CK(cudaSetDevice(device));
+    for (int f = 0; f <= n_files; f++) if (off[f] % 188 || (f && off[f] < off[f - 1])) return fail(EF_EINVAL, "offsets must be non-decreasing multiples of 188");
+    const uint64_t total = off[n_files] - off[0], n_packets = total / 188;
+    std::vector<uint64_t> poff((size_t)n_files + 1);
+    for (int f = 0; f <= n_files; f++) poff[f] = (off[f] - off[0]) / 188;
+    DevBuf d_ts, d_pts, d_kind, d_off, d_spts, d_spos, d_info;
+    CK(d_ts.alloc(total)); CK(d_pts.alloc(n_packets * 8)); CK(d_kind.alloc(n_packets)); CK(d_off.alloc(poff.size() * 8));
+    CK(d_spts.alloc(n_packets * 8)); CK(d_spos.alloc(n_packets * 4)); CK(d_info.alloc((size_t)n_files * 24));
+    CK(cudaMemcpy(d_ts.p, ts + off[0], total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off.p, poff.data(), poff.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_spts.p, 0, n_packets * 8 + (n_packets ? 0 : 1)));
+    CK(cudaMemset(d_spos.p, 0, n_packets * 4 + (n_packets ? 0 : 1)));
+    if (n_packets) {
+        ef_tsidx_packet_kernel<<<(unsigned)((n_packets + 255) / 256), 256>>>((const uint8_t*)d_ts.p, (const uint64_t*)d_off.p, n_files, n_packets, (int64_t*)d_pts.p, (uint8_t*)d_kind.p);
+        CK(cudaGetLastError());
+    }
+    ef_tsidx_compact_kernel<<<n_files, 256>>>((const uint64_t*)d_off.p, (const int64_t*)d_pts.p, (const uint8_t*)d_kind.p,
+                                              (int64_t*)d_spts.p, (uint32_t*)d_spos.p, (int64_t*)d_info.p);
+    CK(cudaGetLastError());
+    std::vector<int64_t> hinfo((size_t)n_files * 3);
+    CK(cudaMemcpy(hinfo.data(), d_info.p, hinfo.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(seq_pts, d_spts.p, n_packets * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(seq_pos, d_spos.p, n_packets * 4, cudaMemcpyDeviceToHost));
+    for (int f = 0; f < n_files; f++) {
+        info[f].first_pts = hinfo[f * 3]; info[f].last_pts = hinfo[f * 3 + 1]; info[f].n_seq = (uint32_t)hinfo[f * 3 + 2];
+        info[f].n_samples = tsidx_sample_count(info[f].n_seq, info[f].first_pts, info[f].last_pts, bin_size);
+    }
+    return EF_OK;
+}
+
+int ef_tsidx_samples(int device, const int64_t* seq_pts, const uint32_t* seq_pos, int n_seq, int64_t first_pts, int64_t last_pts,
+                     uint32_t bin_size, uint32_t* samples, uint32_t cap, uint32_t* n_samples)
+{
+    if (!n_samples || n_seq < 0 || (n_seq && (!seq_pts || !seq_pos))) return fail(EF_EINVAL, "null argument");
+    const uint32_t n = tsidx_sample_count((uint32_t)n_seq, first_pts, last_pts, bin_size);
+    *n_samples = n;
+    if (!n) return EF_OK;
+    if (!samples || cap < n) return fail(EF_ENOMEM, "%u samples needed, capacity %u", n, cap);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= device) return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", device, cudaGetErrorString(e));
+    CK(cudaSetDevice(device));
+    DevBuf d_pts, d_pos, d_out;
+    CK(d_pts.alloc((size_t)n_seq * 8)); CK(d_pos.alloc((size_t)n_seq * 4)); CK(d_out.alloc((size_t)n * 4));
+    CK(cudaMemcpy(d_pts.p, seq_pts, (size_t)n_seq * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_pos.p, seq_pos, (size_t)n_seq * 4, cudaMemcpyHostToDevice));
+    ef_tsidx_sample_kernel<<<(n + 127) / 128, 128>>>((const int64_t*)d_pts.p, (const uint32_t*)d_pos.p, n_seq, first_pts, bin_size, n, (uint32_t*)d_out.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(samples, d_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
 
 }  // extern "C"

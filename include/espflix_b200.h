@@ -142,6 +142,23 @@ int ef_blit(ef_ctx* ctx, int stream_index, int fb, uint16_t* dst, int line, int 
 /* Launch counter: kernels this library has launched since ef_create (bench.py "gpu_launches"). */
 uint64_t ef_launch_count(ef_ctx* ctx);
 
+/* ---- trick-mode index: the reference's offline tool, indexer/indexer.cpp -------------------
+ * Stateless (no context); host buffers; the scans run on `device`.
+ * ef_tsidx_scan     make_index() (indexer.cpp:90-187) for n_files transport streams packed back to back
+ *                   (off[n_files + 1], multiples of 188): the table of (PES pts, TS packet number) of the
+ *                   video packets whose PES payload starts with a sequence header, first_pts (pts of the first,
+ *                   -1 if none) and last_pts (pts of the last video PES start, -1 if none). The table of file f
+ *                   is written at seq_pts/seq_pos[off[f] / 188 ...] (capacity = packets of the file).
+ *                   info[f].n_samples = what pts2seq() will produce for bin_size.
+ * ef_tsidx_samples  pts2seq() + pts2pos() (indexer.cpp:193-228): one uint32 packet number per bin_size ticks
+ *                   from first_pts to last_pts, nearest table entry in pts (the reference's tie-breaking and its
+ *                   int-cast distance). n_seq == 0 yields no samples (the reference indexes an empty vector). */
+typedef struct { int64_t first_pts, last_pts; uint32_t n_seq, n_samples; } ef_tsidx_info;
+int ef_tsidx_scan(int device, const uint8_t* ts, const uint64_t* off, int n_files, uint32_t bin_size,
+                  ef_tsidx_info* info, int64_t* seq_pts, uint32_t* seq_pos);
+int ef_tsidx_samples(int device, const int64_t* seq_pts, const uint32_t* seq_pos, int n_seq, int64_t first_pts, int64_t last_pts,
+                     uint32_t bin_size, uint32_t* samples, uint32_t cap, uint32_t* n_samples);
+
 #ifdef __cplusplus
 }
 #endif

@@ -778,3 +778,106 @@ void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uin
 {
     efo_field_ex(v, strips, strips, frame_counter, 0, NULL, 0, 0, out);
 }
+
+
+/* ================================================================================================
+ * Trick-mode index (indexer/indexer.cpp). TEST INFRASTRUCTURE like the rest of this file.
+ * ================================================================================================ */
+static uint32_t idx_byte(const uint8_t* ts, size_t len, size_t i) { return i < len ? ts[i] : 0u; }
+static uint32_t idx_be16(const uint8_t* ts, size_t len, size_t i) { return (idx_byte(ts, len, i) << 8) | idx_byte(ts, len, i + 1); }
+
+/* parse_pts(), indexer.cpp:43-51 */
+static int64_t idx_parse_pts(const uint8_t* ts, size_t len, size_t d, int flags)
+{
+    flags = (flags >> 2) & 0x30;
+    if ((int)(idx_byte(ts, len, d) & 0xF0) != flags) return -1;
+    int64_t n = ((int64_t)(idx_byte(ts, len, d) & 0x0E)) << 29;
+    n += (int64_t)((idx_be16(ts, len, d + 1) >> 1) << 15);
+    return n + (int64_t)(idx_be16(ts, len, d + 3) >> 1);
+}
+
+/* parse(), indexer.cpp:53-75: returns the 4th payload byte (the start-code value), sets pts */
+static int idx_parse(const uint8_t* ts, size_t len, size_t d, int64_t* pts)
+{
+    *pts = 0;
+    d += 6;
+    const int flags = (int)idx_be16(ts, len, d);
+    const size_t payload = d + 3 + idx_byte(ts, len, d + 2);
+    d += 3;
+    if (flags & 0x0080) *pts = idx_parse_pts(ts, len, d, flags);
+    return (int)idx_byte(ts, len, payload + 3);
+}
+
+int efo_make_index(const uint8_t* ts, size_t len, int64_t* pts_out, uint32_t* pos_out, int cap, int64_t* first_pts, int64_t* last_pts)
+{
+    int n = 0;
+    int64_t origin = -1, video_pts = -1;
+    uint32_t packet = 0;
+    for (size_t i = 0; i + 188 <= len; i += 188, packet++) {          /* indexer.cpp:121-171 */
+        const uint8_t* d = ts + i;
+        const int pid = ((d[1] << 8) + d[2]) & 0x1fff;
+        size_t data = i + 4;
+        if (d[3] & 0x20) data = i + 5 + d[4];                          /* adaptation field */
+        if ((d[3] & 0x10) && (d[1] & 0x40) && pid == 0x100) {          /* has data, payload unit start, video */
+            int64_t pts;
+            const int m = idx_parse(ts, len, data, &pts);
+            if (m == 0xB3) {                                           /* start of sequence */
+                if (origin == -1) origin = pts;
+                if (n < cap) { pts_out[n] = pts; pos_out[n] = packet; }
+                n++;
+            }
+            video_pts = pts;
+        }
+    }
+    *first_pts = origin; *last_pts = video_pts;
+    return n;
+}
+
+int efo_pts2seq(const int64_t* pts, const uint32_t* pos188, int n, int64_t first_pts, int64_t last_pts, uint32_t bin_size,
+                uint32_t* samples, int cap)
+{
+    if (n <= 0 || bin_size == 0) return 0;
+    const int64_t end = last_pts - first_pts;
+    int count = 0;
+    for (int64_t t = 0; t <= end; t += bin_size, count++) {            /* indexer.cpp:211-216 */
+        const int64_t want = t + first_pts;
+        int mini = 0, mine = 0x7FFFFFF;                                /* pts2pos(), indexer.cpp:193-207 */
+        for (int i = 0; i < n; i++) {
+            int64_t diff = pts[i] - want;
+            if (diff < 0) diff = -diff;
+            const int e = (int)diff;
+            if (e < mine) { mine = e; mini = i; }
+        }
+        if (count < cap) samples[count] = pos188[mini];
+    }
+    return count;
+}
+
+size_t efo_build_idx(const uint8_t* const ts[3], const size_t len[3], uint8_t* out, size_t cap)
+{
+    /* idx_hdr (indexer.cpp:22-36): sig, len, then three idx_rec {i64 first, i64 last, u32 bin, u32 speed, u32 count, pad} */
+    size_t total = 104;
+    uint32_t counts[3];
+    for (int k = 0; k < 3; k++) {
+        const int np = (int)(len[k] / 188) + 1;
+        int64_t* pts = (int64_t*)malloc(sizeof(int64_t) * (size_t)np);
+        uint32_t* pos = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)np);
+        int64_t first, last;
+        const int n = efo_make_index(ts[k], len[k], pts, pos, np, &first, &last);
+        const uint32_t bin = 90000 / 12, speed = k == 0 ? 1u : 15u;
+        const int cnt = efo_pts2seq(pts, pos, n, first, last, bin, NULL, 0);
+        counts[k] = (uint32_t)cnt;
+        if (total + 4 * (size_t)cnt <= cap) {
+            efo_pts2seq(pts, pos, n, first, last, bin, (uint32_t*)(out + total), cnt);
+            uint8_t* r = out + 8 + 32 * k;
+            memset(r, 0, 32);
+            memcpy(r, &first, 8); memcpy(r + 8, &last, 8); memcpy(r + 16, &bin, 4); memcpy(r + 20, &speed, 4); memcpy(r + 24, &counts[k], 4);
+        }
+        total += 4 * (size_t)cnt;
+        free(pts); free(pos);
+    }
+    if (total > cap) return 0;
+    const uint32_t sig = ('I' << 0) | ('D' << 8) | ('X' << 16), three = 3;
+    memcpy(out, &sig, 4); memcpy(out + 4, &three, 4);
+    return total;
+}

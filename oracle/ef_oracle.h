@@ -80,6 +80,20 @@ void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uin
 void efo_field_ex(const efo_video* v, const uint8_t* strips_a, const uint8_t* strips_b, int frame_counter, int hscroll,
                   const uint8_t* bitmap, int blend, int progress, uint16_t* out);
 
+/* ---- trick-mode index (indexer/indexer.cpp:90-253) --------------------------------------
+ * make_index(): table of (PES pts, TS packet number) of every video packet that starts a PES whose payload
+ * begins with a sequence header; first_pts = pts of the first one (-1: none), last_pts = pts of the last video
+ * PES start (-1: none). len must be a multiple of 188. Returns the number of table entries (stores <= cap). */
+int efo_make_index(const uint8_t* ts, size_t len, int64_t* pts, uint32_t* pos188, int cap, int64_t* first_pts, int64_t* last_pts);
+/* pts2seq() + pts2pos(): one sample per bin_size ticks from 0 to last-first: the packet number of the table
+ * entry nearest in pts (first minimum; distance cast to int, entries at >= 0x7FFFFFF ticks never win, which
+ * leaves entry 0). n == 0 gives no samples (the reference indexes an empty vector there). Returns the count. */
+int efo_pts2seq(const int64_t* pts, const uint32_t* pos188, int n, int64_t first_pts, int64_t last_pts, uint32_t bin_size,
+                uint32_t* samples, int cap);
+/* merge_index(): the video.idx image for (main, fast-forward, rewind) streams; struct padding bytes (which the
+ * reference leaves indeterminate) are zero here. Returns the image size, 0 if cap is too small. */
+size_t efo_build_idx(const uint8_t* const ts[3], const size_t len[3], uint8_t* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

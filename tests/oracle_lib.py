@@ -13,6 +13,8 @@ I420 = 101376
 FRAME = 101376
 REF_DECODE = os.path.join(ROOT, "oracle", "_ref", "efref_decode")
 REF_VIDEO = os.path.join(ROOT, "oracle", "_ref", "libefref_vid.so")
+REF_INDEX = os.path.join(ROOT, "oracle", "_ref", "libefref_idx.so")
+IDX_PAD = [36, 37, 38, 39, 68, 69, 70, 71, 100, 101, 102, 103]      # padding bytes of idx_hdr (indeterminate in the reference)
 
 
 class _Video(ctypes.Structure):
@@ -46,6 +48,12 @@ class Oracle:
         L.efo_field.argtypes = [VP, VP, ctypes.c_int, VP]
         L.efo_field_ex.argtypes = [VP, VP, VP, ctypes.c_int, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, VP]
         L.efo_stats_get.argtypes = [VP]
+        L.efo_make_index.restype = ctypes.c_int
+        L.efo_make_index.argtypes = [VP, ctypes.c_size_t, VP, VP, ctypes.c_int, VP, VP]
+        L.efo_pts2seq.restype = ctypes.c_int
+        L.efo_pts2seq.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, VP, ctypes.c_int]
+        L.efo_build_idx.restype = ctypes.c_size_t
+        L.efo_build_idx.argtypes = [VP, VP, VP, ctypes.c_size_t]
         self._video = {}
 
     def demux_ts(self, ts):
@@ -123,6 +131,33 @@ class Oracle:
         self.lib.efo_stats_get(ctypes.byref(s))
         return s
 
+    # -- trick-mode index (indexer/indexer.cpp) ----------------------------------------------------------
+    def make_index(self, ts):
+        ts = np.ascontiguousarray(np.frombuffer(bytes(ts), dtype=np.uint8))
+        cap = ts.size // 188 + 1
+        pts, pos = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.uint32)
+        first, last = ctypes.c_int64(), ctypes.c_int64()
+        n = self.lib.efo_make_index(ts.ctypes.data, ts.size, pts.ctypes.data, pos.ctypes.data, cap, ctypes.byref(first), ctypes.byref(last))
+        return {"first_pts": first.value, "last_pts": last.value, "seq_pts": pts[:n].copy(), "seq_pos": pos[:n].copy()}
+
+    def pts2seq(self, seq_pts, seq_pos, first_pts, last_pts, bin_size):
+        seq_pts = np.ascontiguousarray(seq_pts, dtype=np.int64)
+        seq_pos = np.ascontiguousarray(seq_pos, dtype=np.uint32)
+        n = self.lib.efo_pts2seq(seq_pts.ctypes.data, seq_pos.ctypes.data, len(seq_pts), first_pts, last_pts, bin_size, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self.lib.efo_pts2seq(seq_pts.ctypes.data, seq_pos.ctypes.data, len(seq_pts), first_pts, last_pts, bin_size, out.ctypes.data, n)
+        return out[:n].copy()
+
+    def build_idx(self, files):
+        bufs = [np.ascontiguousarray(np.frombuffer(bytes(f), dtype=np.uint8)) for f in files]
+        ptrs = (ctypes.c_void_p * 3)(*[b.ctypes.data for b in bufs])
+        lens = (ctypes.c_size_t * 3)(*[b.size for b in bufs])
+        cap = 104 + 4 * sum(b.size // 188 + 2 for b in bufs) + (1 << 22)
+        out = np.zeros(cap, dtype=np.uint8)
+        n = self.lib.efo_build_idx(ptrs, lens, out.ctypes.data, cap)
+        assert n
+        return out[:n].tobytes()
+
 
 def have_ref():
     return os.path.exists(REF_DECODE) and os.path.exists(REF_VIDEO)
@@ -183,3 +218,41 @@ class RefVideo:
         out = np.zeros(2 * 352 + 160, dtype=np.uint16)
         self.lib.efref_blit(i420.ctypes.data, frame_counter, out.ctypes.data, line, x, width)
         return out
+
+
+def have_ref_index():
+    return os.path.exists(REF_INDEX)
+
+
+class RefIndexer:
+    """The UNMODIFIED reference index builder (oracle/_ref/libefref_idx.so; indexer/indexer.cpp)."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(REF_INDEX)
+        VP = ctypes.c_void_p
+        self.lib.efref_make_index.restype = ctypes.c_int
+        self.lib.efref_make_index.argtypes = [ctypes.c_char_p, VP, VP, ctypes.c_int, VP, VP]
+        self.lib.efref_build_idx.argtypes = [ctypes.c_char_p] * 4
+
+    def make_index(self, ts):
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "in.ts")
+            open(p, "wb").write(bytes(ts))
+            cap = len(bytes(ts)) // 188 + 1
+            pts, pos = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.uint32)
+            first, last = ctypes.c_int64(), ctypes.c_int64()
+            n = self.lib.efref_make_index(p.encode(), pts.ctypes.data, pos.ctypes.data, cap, ctypes.byref(first), ctypes.byref(last))
+            return {"first_pts": first.value, "last_pts": last.value, "seq_pts": pts[:n].copy(), "seq_pos": pos[:n].copy()}
+
+    def build_idx(self, files):
+        """video.idx as the reference tool writes it, padding bytes zeroed."""
+        with tempfile.TemporaryDirectory() as d:
+            paths = []
+            for k, f in enumerate(files):
+                paths.append(os.path.join(d, "s%d.ts" % k))
+                open(paths[-1], "wb").write(bytes(f))
+            self.lib.efref_build_idx(paths[0].encode(), paths[1].encode(), paths[2].encode(), d.encode())
+            img = bytearray(open(os.path.join(d, "video.idx"), "rb").read())
+            for b in IDX_PAD:
+                img[b] = 0
+            return bytes(img)

@@ -42,6 +42,15 @@ def test_no_cpu_fallback():
     assert "no CPU" in str(e.value) or "CUDA" in str(e.value)
 
 
+def test_index_entry_points_have_no_cpu_fallback_either():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(espflix_b200.EspflixError) as e:
+        espflix_b200.tsidx_scan([b"\x47" + b"\x00" * 187])
+    assert e.value.code == capi.EF_ECUDA
+
+
 def test_product_does_not_touch_the_oracle():
     # nothing under espflix_b200/ may import, link or call anything under oracle/
     bad = []

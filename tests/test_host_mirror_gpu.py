@@ -48,3 +48,12 @@ def test_mirrored_decoder_on_synthetic_pal(tmp_path, oracle):
     want = oracle.decode_ts(ts)
     assert np.array_equal(frames, want)
     assert np.array_equal(field, oracle.field(frames[-1], 0, 0))
+
+
+def test_mirrored_index_builder_on_reference_fixture(tmp_path):
+    """make_index() x 3 + merge_index() with the reference tool's own signatures (espflix_b200/host/ef_indexer.h):
+    the video.idx it writes equals the image the unmodified reference tool produced for the same three streams."""
+    paths = [os.path.join(G, n + ".ts") for n in ("vmedia", "splash", "vmedia")]
+    subprocess.run([ef_build.INDEXER_CLI] + paths + [str(tmp_path)], capture_output=True, timeout=600, check=True)
+    got = open(os.path.join(str(tmp_path), "video.idx"), "rb").read()
+    assert got == open(os.path.join(G, "video_idx_fixture.bin"), "rb").read()
