@@ -65,6 +65,17 @@ extern int _video_composite_progress;
 typedef void (*ef_push_video_hook)(Frame* f, int front, int64_t pts, int mode, void* user);
 void ef_set_push_video_hook(ef_push_video_hook hook, void* user);
 
+// Offline presentation pacing (video.cpp:1023-1057 against the flip in video_isr :1165-1177). When enabled,
+// push_video() computes the display field from the PTS exactly like the reference, queues the frame, and then
+// - instead of blocking on VIDEO_READY while a hardware interrupt runs - drives video_isr() itself until the
+// frame has become the current one: time only passes while the decoder waits for presentation ("instant
+// decoder"). Every completed field (line_count x line_width uint16) is handed to `sink` with the value of
+// _frame_counter it was drawn under. mode != 0 shows the frame at once (as the reference) but the poster
+// scroll animation (_easd) is not reproduced.
+typedef void (*ef_field_sink)(const uint16_t* field, int line_width, int line_count, uint32_t frame_counter, void* user);
+void ef_set_video_pacing(int on, ef_field_sink sink, void* user);
+void ef_video_set_frame_counter(int frame_counter);     // _frame_counter at power-up is 0; tests start elsewhere
+
 struct ef_decoder_impl;
 
 class MpegDecoder {

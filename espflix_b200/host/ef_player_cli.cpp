@@ -2,7 +2,8 @@
 // own app drives the original (espflix.cpp:723-737 decode_next; the test harness for the unmodified
 // reference follows the same protocol):
 // pop_empty -> fill Buffer with <= 8 TS packets -> push_full, decoder thread in run(), frames
-// captured from push_video, final flush_picture(1). Usage: ef_player_cli in.ts out.i420 [fields.u16 ntsc]
+// captured from push_video, final flush_picture(1). Usage: ef_player_cli in.ts out.i420 [field.u16 ntsc]
+//   or, with the offline PTS -> field pacing: ef_player_cli in.ts out.i420 --paced fields.u16 ntsc frame_counter0 max_fields
 #include <stdio.h>
 #include <string.h>
 
@@ -13,6 +14,18 @@
 
 static std::vector<uint8_t> g_out;
 static long g_frames = 0;
+
+static std::vector<uint16_t> g_fields;
+static long g_n_fields = 0, g_max_fields = 0;
+static std::vector<uint32_t> g_flip_field;
+static uint32_t g_last_fc = 0;
+
+static void on_field(const uint16_t* field, int w, int lines, uint32_t fc, void*)
+{
+    if (g_n_fields < g_max_fields) g_fields.insert(g_fields.end(), field, field + (size_t)w * lines);
+    g_n_fields++;
+    g_last_fc = fc;
+}
 
 static void on_push(Frame* f, int front, int64_t, int, void*)
 {
@@ -37,6 +50,13 @@ int main(int argc, char** argv)
     fclose(f);
 
     ef_set_push_video_hook(on_push, nullptr);
+    const bool paced = argc >= 8 && !strcmp(argv[3], "--paced");
+    if (paced) {
+        video_init(atoi(argv[5]));
+        ef_video_set_frame_counter(atoi(argv[6]));
+        g_max_fields = atol(argv[7]);
+        ef_set_video_pacing(1, on_field, nullptr);
+    }
     Frame fb[2];
     fb[0].init(); fb[1].init();
     MpegDecoder dec(&fb[0], &fb[1]);
@@ -60,6 +80,16 @@ int main(int argc, char** argv)
     FILE* o = fopen(argv[2], "wb");
     fwrite(g_out.data(), 1, g_out.size(), o);
     fclose(o);
+    if (paced) {
+        // the field in which the last frame flipped is completed by the line interrupt, as it would be on air
+        std::vector<uint16_t> line(1136 + 64);
+        while (_line_counter != 0) video_isr(line.data());
+        FILE* ff = fopen(argv[4], "wb");
+        fwrite(g_fields.data(), 2, g_fields.size(), ff);
+        fclose(ff);
+        printf("{\"frames\": %ld, \"fields\": %ld}\n", g_frames, g_n_fields);
+        return 0;
+    }
     if (argc >= 5) {                               // one field of the last presented frame through video_isr
         const int ntsc = atoi(argv[4]);
         video_init(ntsc);

@@ -2,7 +2,8 @@
 // the C-ABI: video_init, push_video, video_isr (one scan line per call) and blit. A whole field is
 // synthesised on the GPU by one K2 launch when the line counter wraps; video_isr then hands out its
 // lines one by one, so a caller that drives the reference's I2S end-of-line interrupt loop
-// (video.cpp:51-56) is served unchanged. No real-time pacing.
+// (video.cpp:51-56) is served unchanged. No real-time pacing; the PTS -> field schedule of
+// push_video is available offline (ef_set_video_pacing).
 #include <stdio.h>
 #include <string.h>
 
@@ -17,6 +18,9 @@ int16_t _hscroll = 0;
 uint8_t _video_composite[VIDEO_COMPOSITE_HEIGHT * VIDEO_COMPOSITE_WIDTH];
 int _video_composite_blend = 0;
 int _video_composite_progress = 0;
+int8_t _next_frame = -1;                  // video.cpp:936
+uint32_t _next_frame_time = 0;
+uint32_t _video_pts = 0, _pts_origin = 0, _video_frame_counter_origin = 0;   // video.cpp:945-948
 
 namespace {
 ef_ctx* g_ctx = nullptr;
@@ -27,6 +31,10 @@ std::vector<uint16_t> g_field;
 std::vector<uint8_t> g_staging(EF_FRAME_BYTES);
 ef_push_video_hook g_hook = nullptr;
 void* g_hook_user = nullptr;
+bool g_pacing = false, g_dirty = false;
+ef_field_sink g_sink = nullptr;
+void* g_sink_user = nullptr;
+std::vector<uint16_t> g_emitted;
 
 bool ensure_ctx()
 {
@@ -46,6 +54,8 @@ void upload(Frame* f, int fb = 0)
 }  // namespace
 
 void ef_set_push_video_hook(ef_push_video_hook hook, void* user) { g_hook = hook; g_hook_user = user; }
+void ef_set_video_pacing(int on, ef_field_sink sink, void* user) { g_pacing = on != 0; g_sink = sink; g_sink_user = user; }
+void ef_video_set_frame_counter(int frame_counter) { _frame_counter = frame_counter; }
 
 void video_init(int ntsc)                         // video.cpp:572
 {
@@ -57,14 +67,42 @@ void video_init(int ntsc)                         // video.cpp:572
     _line_counter = 0;
 }
 
-void video_reset() {}
+void video_reset()                                  // video.cpp:1070
+{
+    _pts_origin = _video_frame_counter_origin = _video_pts = 0;
+}
 void video_pause(int) {}
 void push_audio(const uint8_t*, int, int64_t, bool) {}   // audio side-chain is out of scope
 
-void push_video(Frame* f, int front, int64_t pts, int mode)   // video.cpp:1023 without the wait on VIDEO_READY
+void push_video(Frame* f, int front, int64_t pts, int mode)   // video.cpp:1023
 {
     g_frames = f;
-    g_current = front;
+    if (!g_pacing) {                               // throughput build: the frame is current at once, nothing waits
+        g_current = front;
+        if (g_hook) g_hook(f, front, pts, mode, g_hook_user);
+        return;
+    }
+    pts /= g_ntsc ? 1500 : 1800;                   // convert to frame counter counts
+    _video_pts = (uint32_t)pts;
+    if (_video_frame_counter_origin == 0) {
+        _pts_origin = _video_pts;
+        _video_frame_counter_origin = (uint32_t)_frame_counter;
+    }
+    uint32_t d = (_video_pts - _pts_origin) + _video_frame_counter_origin;    // when to display
+    if (mode) d = (uint32_t)_frame_counter;        // force immediate for displaying posters etc
+    if (d < (uint32_t)_frame_counter) {
+        const int late = (int)((uint32_t)_frame_counter - d);
+        printf("v late:%d\n", late);
+        if (late > 2) {
+            printf("resetting v timing\n");
+            _video_frame_counter_origin = 0;
+        }
+    }
+    _next_frame_time = d;
+    _next_frame = (int8_t)front;
+    // wait_events(VIDEO_READY): the line interrupt runs until it has flipped to this frame
+    std::vector<uint16_t> line((size_t)g_line_width + 64);
+    while (_next_frame != -1) video_isr(line.data());
     if (g_hook) g_hook(f, front, pts, mode, g_hook_user);
 }
 
@@ -73,7 +111,19 @@ extern "C" void video_isr(volatile void* vbuf)    // video.cpp:1122
     if (!ensure_ctx()) return;
     if (g_field.empty()) video_init(1);
     const int i = _line_counter;
-    if (i == 0) {                                  // new field: one K2 launch
+    {   // flip buffers in blanking (video.cpp:1165-1177): every line that is neither an active line of a
+        // presented frame nor a vertical-sync line checks the queued frame
+        const int active_top = 32 + (g_ntsc ? 0 : 32), active_bottom = active_top + 192;
+        const int vsync_start = g_line_count - (g_ntsc ? 3 : 8);
+        const bool active = i >= active_top && i < active_bottom && g_current != -1;
+        if (!active && i < vsync_start && _next_frame != -1 && (uint32_t)_frame_counter >= _next_frame_time) {
+            g_current = _next_frame;
+            _next_frame = -1;
+            g_dirty = true;                        // the lines below this one show the new frame
+        }
+    }
+    if (i == 0 || g_dirty) {                       // new field (or new frame inside it): one K2 launch
+        g_dirty = false;
         int fb = -2;                               // no frame presented yet: active lines are blank lines
         if (g_frames && g_current != -1) {
             upload(&g_frames[g_current], 0);
@@ -86,8 +136,13 @@ extern "C" void video_isr(volatile void* vbuf)    // video.cpp:1122
             fprintf(stderr, "video: %s\n", ef_last_error());
     }
     memcpy((void*)vbuf, g_field.data() + (size_t)i * g_line_width, (size_t)g_line_width * 2);
+    if (g_pacing && g_sink) {
+        if (g_emitted.size() != g_field.size()) g_emitted.assign(g_field.size(), 0);
+        memcpy(g_emitted.data() + (size_t)i * g_line_width, (const void*)vbuf, (size_t)g_line_width * 2);
+    }
     _line_counter = i + 1;
     if (_line_counter == g_line_count) {           // end of field (video.cpp:1192-1197)
+        if (g_pacing && g_sink) g_sink(g_emitted.data(), g_line_width, g_line_count, (uint32_t)_frame_counter, g_sink_user);
         _line_counter = 0; _frame_counter = _frame_counter + 1;
         if (_video_composite_blend > 0) --_video_composite_blend;
     }

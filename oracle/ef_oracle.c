@@ -881,3 +881,47 @@ size_t efo_build_idx(const uint8_t* const ts[3], const size_t len[3], uint8_t* o
     memcpy(out, &sig, 4); memcpy(out + 4, &three, 4);
     return total;
 }
+
+
+/* ================================================================================================
+ * PTS -> field pacing (video.cpp:1023-1057, 1122-1198), instant-decoder model.
+ * ================================================================================================ */
+long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int ntsc, uint32_t frame_counter0, long max_fields,
+                        uint32_t* flip_field, int* flip_line)
+{
+    const int line_count = ntsc ? 262 : 312;
+    const int active_top = 32 + (ntsc ? 0 : 32), active_bottom = active_top + 192;      /* video.cpp:1135-1137 */
+    const int vsync_start = line_count - (ntsc ? 3 : 8);
+    uint32_t frame_counter = frame_counter0;
+    uint32_t video_pts, pts_origin = 0, fc_origin = 0, next_time = 0;
+    int current = -1, next = -1, k = 0;
+    long fields = 0;
+    while (fields < max_fields) {
+        for (int i = 0; i < line_count; i++) {
+            if (next == -1 && k < n_frames) {                         /* push_video(k), video.cpp:1023 */
+                int64_t p = pts[k] / (ntsc ? 1500 : 1800);
+                video_pts = (uint32_t)p;
+                if (fc_origin == 0) { pts_origin = video_pts; fc_origin = frame_counter; }
+                uint32_t d = (video_pts - pts_origin) + fc_origin;
+                if (modes && modes[k]) d = frame_counter;           /* force immediate, video.cpp:1039 */
+                if (d < frame_counter) {
+                    const int late = (int)(frame_counter - d);
+                    if (late > 2) fc_origin = 0;                       /* "resetting v timing" */
+                }
+                next_time = d; next = k & 1;
+            }
+            const int active = i >= active_top && i < active_bottom && current != -1;
+            if (!active && i < vsync_start) {                          /* the else branch of video_isr: flip buffers in blanking */
+                if (next != -1 && frame_counter >= next_time) {
+                    current = next; next = -1;
+                    flip_field[k] = frame_counter; flip_line[k] = i;
+                    k++;
+                }
+            }
+        }
+        frame_counter++;
+        fields++;
+        if (k >= n_frames && next == -1) break;
+    }
+    return fields;
+}

@@ -80,6 +80,15 @@ void efo_field(const efo_video* v, const uint8_t* strips, int frame_counter, uin
 void efo_field_ex(const efo_video* v, const uint8_t* strips_a, const uint8_t* strips_b, int frame_counter, int hscroll,
                   const uint8_t* bitmap, int blend, int progress, uint16_t* out);
 
+/* ---- PTS -> field pacing (push_video video.cpp:1023-1057 + the flip in video_isr :1165-1177) --------
+ * "Instant decoder" model: frame k is queued the moment frame k-1 became the current frame, and the line
+ * interrupt only advances while a frame is queued. flip_field[k] / flip_line[k] = _frame_counter and line at
+ * which frame k becomes _current_frame. Returns the number of whole fields emitted up to and including the one
+ * in which the last frame flipped (stops at max_fields). modes (may be NULL = all 0): 1 = show at once, as
+ * MpegDecoder::flush_picture(1) pushes the last picture; 2/3 (poster scroll animation) are not modelled. */
+long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int ntsc, uint32_t frame_counter0, long max_fields,
+                        uint32_t* flip_field, int* flip_line);
+
 /* ---- trick-mode index (indexer/indexer.cpp:90-253) --------------------------------------
  * make_index(): table of (PES pts, TS packet number) of every video packet that starts a PES whose payload
  * begins with a sequence header; first_pts = pts of the first one (-1: none), last_pts = pts of the last video

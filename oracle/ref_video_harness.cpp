@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <atomic>
+#include <chrono>
+#include <thread>
 
 #include "player.h"   // reference headers: Frame, video_init, ...
 #undef printf
@@ -28,6 +31,9 @@ extern volatile int _line_counter;
 extern volatile int _frame_counter;
 extern int _line_count, _line_width, _hsync, _hsync_long, _hsync_short, _burst_start, _burst_width, _active_start;
 extern int8_t _next_frame, _current_frame;
+extern uint32_t _next_frame_time;
+void video_reset();
+void push_video(Frame* f, int front, int64_t pts, int mode);   // video.cpp:1023
 extern int16_t _hscroll;
 extern Frame* _frames;
 extern uint32_t _color_tab[256 * 3];
@@ -125,6 +131,61 @@ void efref_blit(const uint8_t* i420, int frame_counter, uint16_t* dst, int line,
     load_i420(&g_fb[0], i420);
     _frame_counter = frame_counter;
     blit(&g_fb[0], dst, line, x, width);
+}
+
+
+// PTS -> field pacing of push_video (video.cpp:1023-1057) against the frame flip of video_isr (:1165-1177),
+// under the "instant decoder" model: a decoder thread pushes frame k the moment push_video(k-1) returns, and
+// the line interrupt (this thread) only advances while a frame is queued or the decoder has finished - i.e.
+// time passes only while the decoder waits for presentation. Deterministic, and the only model an offline
+// throughput build can have. Returns the number of whole fields emitted (<= max_fields); flip_field/flip_line[k]
+// = _frame_counter and line at which frame k became _current_frame. `out` (may be NULL) receives the fields.
+long efref_paced(const uint8_t* i420_frames, int n_frames, const int64_t* pts, const int* modes, int frame_counter0, int max_fields,
+                 uint16_t* out, uint32_t* flip_field, int* flip_line)
+{
+    video_reset();
+    _frames = g_fb; _current_frame = -1; _next_frame = -1; _next_frame_time = 0;
+    _line_counter = 0; _frame_counter = frame_counter0; _hscroll = 0; _video_composite_blend = 0;
+    std::atomic<int> done(0), pushed(0);
+    std::thread decoder([&] {
+        for (int k = 0; k < n_frames; k++) {
+            load_i420(&g_fb[k & 1], i420_frames + (size_t)k * 101376);      // the back buffer, as the decoder would
+            pushed = k + 1;
+            push_video(g_fb, k & 1, pts[k], modes ? modes[k] : 0);          // blocks until the ISR flips (mode 1: MpegDecoder::flush_picture(1))
+        }
+        done = 1;
+    });
+    uint16_t* lb[2];
+    lb[0] = (uint16_t*)calloc(_line_width + 64, 2);
+    lb[1] = (uint16_t*)calloc(_line_width + 64, 2);
+    const int lines = _line_count, w = _line_width;
+    long fields = 0;
+    int flips = 0;
+    bool stuck = false;
+    while (fields < max_fields && !stuck) {
+        for (int l = 0; l < lines && !stuck; l++) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while (_next_frame == -1 && !done) {                            // wait for the decoder to queue its next frame
+                std::this_thread::yield();
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) { stuck = true; break; }
+            }
+            if (stuck) break;
+            const int before = _current_frame;
+            const uint32_t fc = (uint32_t)_frame_counter;
+            video_isr(lb[l & 1]);
+            if (_current_frame != before && flips < n_frames) { flip_field[flips] = fc; flip_line[flips] = l; flips++; }
+            if (out) memcpy(out + ((size_t)fields * lines + l) * w, lb[l & 1], (size_t)w * 2);
+        }
+        fields++;
+        if (done && _next_frame == -1) break;                               // last frame is on screen for this whole field
+    }
+    if (!done) {                                                            // stopped early: never leave the decoder thread parked
+        _frame_counter = 0x7FFFFFF0;
+        for (long guard = 0; guard < 100000000L && !done; guard++) { _line_counter = 0; _next_frame_time = 0; video_isr(lb[0]); std::this_thread::yield(); }
+    }
+    decoder.join();
+    free(lb[0]); free(lb[1]);
+    return stuck ? -1 : fields;
 }
 
 }  // extern "C"

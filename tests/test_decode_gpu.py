@@ -199,3 +199,32 @@ def test_decode_all_multi_picture_parse(oracle, monkeypatch, rec_pics):
         ctx.reset()
         ctx.submit_es(blob, off)
     ctx.close()
+
+
+def test_full_baseline_batch_is_bit_exact(oracle):
+    """The benchmarked configuration itself (BASELINE config 4 = bench.py's workload: 4,096 streams x 12
+    pictures, 64 distinct seeds replicated 64 times, one ef_decode_all): every distinct stream's last two
+    pictures equal the oracle's, and every replica equals its original (no cross-stream interference at the
+    size the throughput number is quoted on)."""
+    import bench
+    gen, streams = bench.make_streams(bench.STREAMS_PER_GPU, 0)
+    d = len(gen)
+    ctx = espflix_b200.Context(n_streams=len(streams), max_pictures=bench.PICTURES, max_slices_per_picture=12,
+                               es_capacity=sum(len(s) for s in streams) + 4096, fields=False)
+    blob, off = ctx.pack(streams)
+    ctx.submit_es(blob, off)
+    ctx.index()
+    info = ctx.index_info()
+    assert info["total_pictures"] == len(streams) * bench.PICTURES and info["total_slices"] == len(streams) * bench.PICTURES * 12
+    ctx.decode_all(bench.PICTURES)
+    got = ctx.read_latest_i420()
+    for i in range(d):
+        want = oracle.decode_es(gen[i][0])
+        assert want.shape[0] == bench.PICTURES
+        assert np.array_equal(got[i], want[-1]), "stream %d last picture: %s" % (i, _first_diff(got[i], want[-1]))
+        base = ctx.stream_info(i)[1]
+        prev = ctx.read_frame_i420(i, ((base + bench.PICTURES) & 1) ^ 1)
+        assert np.array_equal(prev, want[-2]), "stream %d previous picture" % i
+    g = got.reshape(len(streams) // d, d, -1)
+    assert np.array_equal(g, np.broadcast_to(g[0], g.shape)), "a replica differs from its original"
+    ctx.close()

@@ -57,3 +57,23 @@ def test_mirrored_index_builder_on_reference_fixture(tmp_path):
     subprocess.run([ef_build.INDEXER_CLI] + paths + [str(tmp_path)], capture_output=True, timeout=600, check=True)
     got = open(os.path.join(str(tmp_path), "video.idx"), "rb").read()
     assert got == open(os.path.join(G, "video_idx_fixture.bin"), "rb").read()
+
+
+@pytest.mark.parametrize("name", ["ntsc_fc1", "pal_fc5", "ntsc_fc0_quirk"])
+def test_mirrored_presentation_pacing(name, tmp_path):
+    """push_video with the offline PTS -> field pacing (ef_set_video_pacing): the decoder mirror pushes its
+    frames, push_video drives video_isr until each frame has flipped, and the stream of fields that reaches the
+    sink is - sample for sample - what the unmodified reference's push_video + video_isr emit for the same
+    pictures and PTS (tests/golden/pacing_pins.json, instant-decoder model)."""
+    p = json.load(open(os.path.join(G, "pacing_pins.json")))[name]
+    es, off = synth.generate(synth.SEED0 + p["seed"], n_pictures=p["pictures"])
+    ts_path = os.path.join(str(tmp_path), "in.ts")
+    open(ts_path, "wb").write(synth.wrap_ts(es, off).tobytes())
+    out, fields = os.path.join(str(tmp_path), "out.i420"), os.path.join(str(tmp_path), "fields.u16")
+    r = subprocess.run([ef_build.HOST_CLI, ts_path, out, "--paced", fields, str(p["ntsc"]), str(p["frame_counter0"]), str(p["max_fields"])],
+                       capture_output=True, timeout=600, check=True)
+    info = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert info["frames"] == p["pictures"] and info["fields"] == p["fields"]
+    stream = np.fromfile(fields, dtype=np.uint16)
+    assert stream.nbytes == p["stream_bytes"]
+    assert hashlib.sha256(stream.tobytes()).hexdigest() == p["stream_sha256"]
