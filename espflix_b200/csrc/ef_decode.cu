@@ -19,15 +19,16 @@
 //       of the slice in the ES blob): every coefficient costs at least 3 bits of bitstream, so lists
 //       can never run into each other and no allocation or prefix sum is needed.
 //   K1b ef_recon_kernel   records -> pixels, one launch per picture index (P pictures read the
-//       previous picture of their stream). One WARP per macroblock record, all 1,081,344 of a
-//       BASELINE picture batch independent: scatter the list into a dense 6x64 scratch, the
-//       reference's integer AAN IDCT in place (one lane per block column, then per block row), half-pel
-//       motion compensation from reference tiles staged by TMA bulk copies, the clamped add, 8-byte
-//       stores. Records of the next macroblock are prefetched while the current one is rebuilt.
+//       previous picture of their stream). One HALF-WARP per macroblock record (a warp = two
+//       consecutive slots), all 1,081,344 of a BASELINE picture batch independent: scatter the list
+//       into a dense 6x64 scratch, the reference's integer AAN IDCT in place (3 column passes, then 3
+//       row passes of 16 lanes), half-pel motion compensation from reference tiles staged by TMA bulk
+//       copies, the clamped add, 8-byte stores. Records are prefetched one iteration ahead; work
+//       comes from a global cursor.
 //
 //   * frame stores are MACROBLOCK-TILED in HBM (ef_common.cuh): a macroblock is 384 contiguous
-//     bytes, so the warp's stores are two full 128-byte lines + one more for chroma, no partial
-//     sectors; motion-compensated reads touch <= 4 tiles.
+//     bytes, so a half-warp stores one full 128-byte line per row pass, no partial sectors;
+//     motion-compensated reads touch <= 4 tiles.
 // Bit-exactness notes: Q1 clamp [0,248]; Q2 oddification maps 0 -> +1; Q3 chroma
 // vector = floor(luma position / 2); Q4 matrices indexed in raster order (done at index time);
 // Q5 single-coefficient blocks bypass the IDCT with floor; Q6 first macroblock of a slice lands in
