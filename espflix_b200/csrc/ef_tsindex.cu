@@ -29,14 +29,14 @@ __global__ void ef_tsidx_packet_kernel(const uint8_t* __restrict__ ts, const uin
     const uint32_t pid = ((b1 << 8) + b2) & 0x1fff;
     uint8_t kind = 0;
     int64_t pts = 0;
-    if ((b3 & 0x10) && (b1 & 0x40) && pid == 0x100) {                    // has data, payload unit start, video
+    if ((b3 & 0x10) && (b1 & 0x40) && pid == 0x100) {                    // payload present, PES starts here, video PID
         // a PES header cut short by the packet is read on into the following packets of the SAME file (as the
         // reference's buffer would give), zeros behind the end of the file: find the file of this packet
         int lo = 0, hi = n_files;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pkt_off[mid] <= k) lo = mid; else hi = mid; }
         const uint64_t total_bytes = pkt_off[lo + 1] * 188;
         uint64_t d = i + 4;
-        if (b3 & 0x20) d = i + 5 + ts[i + 4];                             // adaptation field
+        if (b3 & 0x20) d = i + 5 + ts[i + 4];                             // skip the adaptation field
         d += 6;                                                           // parse(), indexer.cpp:53
         const int flags = (int)tb16(ts, total_bytes, d);
         const uint64_t payload = d + 3 + tb(ts, total_bytes, d + 2);

@@ -24,7 +24,7 @@ typedef struct {            // indexer.cpp:30
     idx_rec rev;
 } idx_hdr;
 
-typedef struct {            // indexer.cpp:78: 1/4 second mapping of pts to sequence offset
+typedef struct {            // indexer.cpp:78: one sequence header: its PES pts and the TS packet it starts in
     int64_t pts;
     uint32_t pos188;
 } seq;
@@ -36,7 +36,7 @@ typedef struct {            // indexer.cpp:83
     std::vector<uint32_t> samples;
 } idx;
 
-// find all the pts points in the video (indexer.cpp:90); appends one idx to idxs. Throws std::runtime_error
+// scan one transport stream for its sequence headers (indexer.cpp:90); appends one idx to idxs. Throws std::runtime_error
 // when the file cannot be read or the GPU call fails (the reference would crash on fopen failure).
 void make_index(const std::string& src, std::vector<idx>& idxs);
 // indexer.cpp:209: fills id.samples, returns the header record

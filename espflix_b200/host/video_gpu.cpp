@@ -82,14 +82,14 @@ void push_video(Frame* f, int front, int64_t pts, int mode)   // video.cpp:1023
         if (g_hook) g_hook(f, front, pts, mode, g_hook_user);
         return;
     }
-    pts /= g_ntsc ? 1500 : 1800;                   // convert to frame counter counts
+    pts /= g_ntsc ? 1500 : 1800;                   // 90 kHz ticks -> field periods (60 / 50 Hz)
     _video_pts = (uint32_t)pts;
     if (_video_frame_counter_origin == 0) {
         _pts_origin = _video_pts;
         _video_frame_counter_origin = (uint32_t)_frame_counter;
     }
-    uint32_t d = (_video_pts - _pts_origin) + _video_frame_counter_origin;    // when to display
-    if (mode) d = (uint32_t)_frame_counter;        // force immediate for displaying posters etc
+    uint32_t d = (_video_pts - _pts_origin) + _video_frame_counter_origin;    // field counter value at which this frame is due
+    if (mode) d = (uint32_t)_frame_counter;        // any non-zero mode: due now
     if (d < (uint32_t)_frame_counter) {
         const int late = (int)((uint32_t)_frame_counter - d);
         printf("v late:%d\n", late);

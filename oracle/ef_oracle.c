@@ -818,10 +818,10 @@ int efo_make_index(const uint8_t* ts, size_t len, int64_t* pts_out, uint32_t* po
         const int pid = ((d[1] << 8) + d[2]) & 0x1fff;
         size_t data = i + 4;
         if (d[3] & 0x20) data = i + 5 + d[4];                          /* adaptation field */
-        if ((d[3] & 0x10) && (d[1] & 0x40) && pid == 0x100) {          /* has data, payload unit start, video */
+        if ((d[3] & 0x10) && (d[1] & 0x40) && pid == 0x100) {          /* payload present, PES starts here, video PID */
             int64_t pts;
             const int m = idx_parse(ts, len, data, &pts);
-            if (m == 0xB3) {                                           /* start of sequence */
+            if (m == 0xB3) {                                           /* payload begins with a sequence header */
                 if (origin == -1) origin = pts;
                 if (n < cap) { pts_out[n] = pts; pos_out[n] = packet; }
                 n++;
@@ -903,10 +903,10 @@ long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int 
                 video_pts = (uint32_t)p;
                 if (fc_origin == 0) { pts_origin = video_pts; fc_origin = frame_counter; }
                 uint32_t d = (video_pts - pts_origin) + fc_origin;
-                if (modes && modes[k]) d = frame_counter;           /* force immediate, video.cpp:1039 */
+                if (modes && modes[k]) d = frame_counter;           /* non-zero mode: due now, video.cpp:1039 */
                 if (d < frame_counter) {
                     const int late = (int)(frame_counter - d);
-                    if (late > 2) fc_origin = 0;                       /* "resetting v timing" */
+                    if (late > 2) fc_origin = 0;                       /* more than two fields late: re-latch the origin at the next push */
                 }
                 next_time = d; next = k & 1;
             }
