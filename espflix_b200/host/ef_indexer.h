@@ -8,33 +8,27 @@
 #include <string>
 #include <vector>
 
-typedef struct {            // indexer.cpp:22
-    int64_t first_pts;
-    int64_t last_pts;
-    uint32_t bin_size;
-    uint32_t trick_speed;
-    uint32_t sample_count;
-} idx_rec;
+// Layout-compatible with the reference's records (indexer.cpp:22-36, 77-88): video.idx is these structs written raw.
+struct idx_rec {
+    int64_t first_pts, last_pts;                        // pts of the first sequence header / of the last video PES start
+    uint32_t bin_size, trick_speed, sample_count;       // ticks per sample, playback speed of the stream, samples that follow
+};
 
-typedef struct {            // indexer.cpp:30
-    uint32_t sig;
-    uint32_t len;           // 3
-    idx_rec video;
-    idx_rec fwd;
-    idx_rec rev;
-} idx_hdr;
+struct idx_hdr {
+    uint32_t sig, len;                                  // 'I','D','X',0 and the number of records (3)
+    idx_rec video, fwd, rev;                            // main stream, fast-forward and rewind trick streams
+};
 
-typedef struct {            // indexer.cpp:78: one sequence header: its PES pts and the TS packet it starts in
-    int64_t pts;
-    uint32_t pos188;
-} seq;
+struct seq {                                            // one sequence header:
+    int64_t pts;                                        //   PES pts of the packet it starts in
+    uint32_t pos188;                                    //   that packet's number in the file
+};
 
-typedef struct {            // indexer.cpp:83
+struct idx {                                            // everything known about one transport stream
     std::vector<seq> seqs;
-    int64_t first_pts;
-    int64_t last_pts;
-    std::vector<uint32_t> samples;
-} idx;
+    int64_t first_pts, last_pts;
+    std::vector<uint32_t> samples;                      // filled by pts2seq()
+};
 
 // scan one transport stream for its sequence headers (indexer.cpp:90); appends one idx to idxs. Throws std::runtime_error
 // when the file cannot be read or the GPU call fails (the reference would crash on fopen failure).
