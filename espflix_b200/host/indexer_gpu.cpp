@@ -9,6 +9,8 @@
 
 #include "espflix_b200.h"
 
+static_assert(sizeof(idx_rec) == 32 && sizeof(idx_hdr) == 104, "video.idx layout (indexer.cpp:22-36)");
+
 static int g_index_device = 0;
 void ef_indexer_set_device(int device) { g_index_device = device; }
 
