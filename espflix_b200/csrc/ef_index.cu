@@ -105,7 +105,11 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
                 const int i = __ffs(h) - 1;
                 h &= h - 1;
                 const uint64_t pos = obase + i - misalign;                    // first 00 of the start code
-                const uint32_t code = ld_byte(es, len, pos + 3);
+                // the start-code value is byte i + 3 of the owning lane's 20-byte window: a shuffle, not another
+                // dependent global load per start code (the sweep is latency bound, ~170 start codes per stream)
+                const int bi = i + 3;
+                const uint32_t wsel = bi < 4 ? w[0] : bi < 8 ? w[1] : bi < 12 ? w[2] : bi < 16 ? w[3] : w[4];
+                const uint32_t code = __shfl_sync(0xFFFFFFFFu, (wsel >> ((bi & 3) * 8)) & 0xFFu, src);
                 if (code == 0x00) {                                           // picture(), player.cpp:704
                     const uint32_t idx = n_pic++;
                     const uint64_t hb = (pos + 4) * 8;
