@@ -53,6 +53,18 @@ int fail(int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(EF_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Every entry point runs on its context's device whatever the caller's current device is, and leaves the
+// caller's current device as it found it (several contexts on several GPUs may share a host thread).
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev)
+    {
+        if (dev < 0 || cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        if (prev == dev) prev = -1; else cudaSetDevice(dev);
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // device frame stores are macroblock-tiled (ef_common.cuh); these kernels convert to/from the two
 // host-visible layouts: the I420 dump and the reference's strips (video.h:36-44; player.cpp:33-46).
 // mode 0 = I420, 1 = strips. One thread per 8 bytes (8 aligned consecutive bytes never straddle a tile row:
@@ -194,7 +206,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= cfg->device)
         return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", cfg->device, cudaGetErrorString(e));
-    CK(cudaSetDevice(cfg->device));
+    DeviceScope scope_(cfg->device);
     ef_ctx* c = new ef_ctx();
     c->cfg = *cfg;
     cudaDeviceProp prop;
@@ -281,6 +293,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
 
 void ef_destroy(ef_ctx* c)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return;
     cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
@@ -299,6 +312,7 @@ void ef_destroy(ef_ctx* c)
 
 int ef_reset(ef_ctx* c)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
     CK(cudaMemset(c->h.frames, 0, (size_t)c->cfg.n_streams * 2 * EF_FRAME + 1024));     // Frame::init zero-fills (player.cpp:25)
     ef_reset_seq_kernel<<<(c->cfg.n_streams + 127) / 128, 128>>>(c->d, c->d_default_intra);
@@ -316,6 +330,7 @@ int ef_reset(ef_ctx* c)
 // makes the compute stream wait for the upload and flips the buffers.
 static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, bool host, bool ts, cudaStream_t st)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !src || !off) return fail(EF_EINVAL, "null argument");
     const int n = c->cfg.n_streams;
     const int b = c->pending >= 0 ? c->pending : (c->active ^ 1);
@@ -375,6 +390,7 @@ int ef_submit_ts_device(ef_ctx* c, const uint8_t* ts, const uint64_t* off, void*
 
 int ef_index(ef_ctx* c, void* stream)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
     if (!c->submitted) return fail(EF_ESTATE, "ef_index before any submit");
     cudaStream_t st = (cudaStream_t)stream;
@@ -400,6 +416,7 @@ int ef_index(ef_ctx* c, void* stream)
 
 int ef_index_info(ef_ctx* c, int* max_pictures, uint64_t* total_pictures, uint64_t* total_slices, uint64_t* es_bytes)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
     if (!c->indexed) return fail(EF_ESTATE, "ef_index_info before ef_index");
     uint32_t info[8];
@@ -419,6 +436,7 @@ int ef_index_info(ef_ctx* c, int* max_pictures, uint64_t* total_pictures, uint64
 
 int ef_stream_info(ef_ctx* c, int stream_index, int* n_pictures, int* base_pictures)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || stream_index < 0 || stream_index >= c->cfg.n_streams) return fail(EF_EINVAL, "bad stream index");
     uint32_t a = 0, b = 0;
     CK(cudaDeviceSynchronize());
@@ -432,6 +450,7 @@ int ef_stream_info(ef_ctx* c, int stream_index, int* n_pictures, int* base_pictu
 // K1a over picture indices [p0, p0 + k), then K1b once per picture index
 static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     const size_t slots = (size_t)k * c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX;
     CK(cudaMemsetAsync(c->h.mb_info, 0, slots * 4, st));
     CK(cudaMemsetAsync(c->h.parse_cursor, 0, ((size_t)k + 1) * 4, st));
@@ -465,6 +484,7 @@ int ef_decode_all(ef_ctx* c, int n_pictures, void* stream)
 
 int ef_read_frame(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !dst) return fail(EF_EINVAL, "null argument");
     CK(cudaDeviceSynchronize());
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
@@ -480,6 +500,7 @@ int ef_read_frame(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
 
 int ef_read_latest_i420_async(ef_ctx* c, int first, int count, uint8_t* dst, void* stream)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !dst) return fail(EF_EINVAL, "null argument");
     if (first < 0 || count < 1 || first + count > c->cfg.n_streams) return fail(EF_EINVAL, "stream range out of bounds");
     const int k = c->stage_idx ^= 1;
@@ -506,6 +527,7 @@ int ef_read_latest_i420_async(ef_ctx* c, int first, int count, uint8_t* dst, voi
 
 int ef_sync(ef_ctx* c, void* stream)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     CK(cudaStreamSynchronize(c->up_stream));
@@ -523,6 +545,7 @@ int ef_read_latest_i420(ef_ctx* c, int first, int count, uint8_t* dst, void* str
 
 int ef_read_frame_i420(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !dst) return fail(EF_EINVAL, "null argument");
     CK(cudaDeviceSynchronize());
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
@@ -538,6 +561,7 @@ int ef_read_frame_i420(ef_ctx* c, int stream_index, int fb, uint8_t* dst)
 
 int ef_write_frame_i420(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !src) return fail(EF_EINVAL, "null argument");
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
     if (rc != EF_OK) return rc;
@@ -553,6 +577,7 @@ int ef_write_frame_i420(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
 
 int ef_write_frame(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !src) return fail(EF_EINVAL, "null argument");
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
     if (rc != EF_OK) return rc;
@@ -575,6 +600,7 @@ int ef_frame_device_ptr(ef_ctx* c, int stream_index, int fb, void** ptr)
 
 int ef_video_init(ef_ctx* c, int ntsc)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
     EfGeometry g;
     memset(&g, 0, sizeof(g));
@@ -611,6 +637,7 @@ int ef_video_geometry(ef_ctx* c, int* line_width, int* line_count)
 
 int ef_composite_field(ef_ctx* c, int fb, int frame_counter, void* stream)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
     if (!c->h.fields) return fail(EF_ESTATE, "context was created without field buffers (ef_config.fields = 0)");
     if (fb < -2 || fb > 1) return fail(EF_EINVAL, "fb must be 0, 1, -1 or -2");
@@ -629,6 +656,7 @@ int ef_video_set_scroll(ef_ctx* c, int hscroll)
 
 int ef_video_set_overlay(ef_ctx* c, const uint8_t* bitmap, int blend, int progress)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
     if (blend != 0 && !bitmap && c->present.blend == 0) return fail(EF_EINVAL, "overlay bitmap required when blend != 0");
     if (bitmap) { CK(cudaDeviceSynchronize()); CK(cudaMemcpy(c->d_overlay, bitmap, 1280, cudaMemcpyHostToDevice)); }
@@ -638,6 +666,7 @@ int ef_video_set_overlay(ef_ctx* c, const uint8_t* bitmap, int blend, int progre
 
 int ef_read_field(ef_ctx* c, int stream_index, uint16_t* dst)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !dst || stream_index < 0 || stream_index >= c->cfg.n_streams) return fail(EF_EINVAL, "bad argument");
     if (!c->h.fields) return fail(EF_ESTATE, "no field buffers");
     CK(cudaDeviceSynchronize());
@@ -648,6 +677,7 @@ int ef_read_field(ef_ctx* c, int stream_index, uint16_t* dst)
 
 int ef_video_isr(ef_ctx* c, int stream_index, int line, uint16_t* buf)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !buf || stream_index < 0 || stream_index >= c->cfg.n_streams) return fail(EF_EINVAL, "bad argument");
     if (!c->h.fields) return fail(EF_ESTATE, "no field buffers");
     if (line < 0 || line >= c->h.geo.line_count) return fail(EF_EINVAL, "line %d out of range", line);
@@ -659,6 +689,7 @@ int ef_video_isr(ef_ctx* c, int stream_index, int line, uint16_t* buf)
 
 int ef_blit(ef_ctx* c, int stream_index, int fb, uint16_t* dst, int line, int x, int width, int frame_counter)
 {
+    DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !dst) return fail(EF_EINVAL, "null argument");
     if (line < 0 || line >= EF_H || x < 0 || width < 0 || (x & ~3) + width > EF_W) return fail(EF_EINVAL, "blit span out of range");
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
@@ -697,7 +728,7 @@ int ef_tsidx_scan(int device, const uint8_t* ts, const uint64_t* off, int n_file
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= device) return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", device, cudaGetErrorString(e));
-    CK(cudaSetDevice(device));
+    DeviceScope scope_(device);
     for (int f = 0; f <= n_files; f++) if (off[f] % 188 || (f && off[f] < off[f - 1])) return fail(EF_EINVAL, "offsets must be non-decreasing multiples of 188");
     const uint64_t total = off[n_files] - off[0], n_packets = total / 188;
     std::vector<uint64_t> poff((size_t)n_files + 1);
@@ -738,7 +769,7 @@ int ef_tsidx_samples(int device, const int64_t* seq_pts, const uint32_t* seq_pos
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= device) return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", device, cudaGetErrorString(e));
-    CK(cudaSetDevice(device));
+    DeviceScope scope_(device);
     DevBuf d_pts, d_pos, d_out;
     CK(d_pts.alloc((size_t)n_seq * 8)); CK(d_pos.alloc((size_t)n_seq * 4)); CK(d_out.alloc((size_t)n * 4));
     CK(cudaMemcpy(d_pts.p, seq_pts, (size_t)n_seq * 8, cudaMemcpyHostToDevice));
