@@ -22,8 +22,11 @@
  *                                 (player.cpp:658-724), done once per submit for the whole batch
  *   ef_decode_picture             MpegDecoder::slice() player.cpp:1251 and everything under it
  *                                 (block/idct/mocomp/predict/copy_block..., player.cpp:733-1236) for
- *                                 picture #pic of every stream: ONE fused kernel launch
- *   ef_decode_all                 the for(;;) of MpegDecoder::run() player.cpp:1355 over one submit
+ *                                 picture #pic of every stream: one parse launch (slice/block: bitstream ->
+ *                                 macroblock records) + one reconstruction launch (idct/mocomp/copy_block)
+ *   ef_decode_all                 the for(;;) of MpegDecoder::run() player.cpp:1355 over one submit: every
+ *                                 slice of every picture is parsed in ONE launch, then one reconstruction
+ *                                 launch per picture index
  *   ef_read_frame / _i420         what push_video(Frame*,front,pts,mode) video.h:49 hands to the
  *                                 display side: the striped Frame (video.h:36-44) of one stream
  *   ef_video_init                 video_init(int ntsc) video.cpp:572
@@ -31,6 +34,10 @@
  *                                 blit video.cpp:690, blanking, vsync) for every stream: ONE launch
  *   ef_read_field / ef_video_isr  the uint16 line buffer video_isr(volatile void*) fills
  *   ef_blit                       blit(Frame*,uint16_t*,line,x,width) video.cpp:690
+ *   ef_video_set_scroll / _overlay  _hscroll video.cpp:1146-1154, composite() video.cpp:839-887
+ *   ef_tsidx_scan                 make_index(const string&, vector<idx>&) indexer/indexer.cpp:90
+ *   ef_tsidx_samples              pts2seq(idx&,int,int) + pts2pos indexer/indexer.cpp:193-228
+ * Calls run on the context's device and restore the caller's current device.
  */
 #ifndef ESPFLIX_B200_H
 #define ESPFLIX_B200_H
