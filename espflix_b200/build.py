@@ -50,6 +50,15 @@ def build_cuda(force=False, verbose_ptxas=False):
     return ""
 
 
+def build_variant(tag, defs):
+    """Tuning variant of the CUDA library with extra nvcc definitions: espflix_b200/libespflix_b200.<tag>.so
+    (selected at run time with EF_LIB). Used by tools/sweep_variants.py; never the product."""
+    srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
+    out = os.path.join(PKG, "libespflix_b200.%s.so" % tag)
+    _run([nvcc_path()] + list(NVCC_FLAGS) + defs.split() + ["-o", out] + srcs, cwd=CSRC)
+    return out
+
+
 def build_synth(force=False):
     src = os.path.join(PKG, "synth", "efsynth.cpp")
     if force or _newer(SYNTH_LIB, [src, os.path.join(CSRC, "ef_iso11172_tables.h")]):

@@ -23,6 +23,11 @@ class _Config(ctypes.Structure):
 
 
 def lib_path():
+    """The CUDA library. EF_LIB (a file name inside the package directory, or an absolute path) selects a tuning
+    variant built by espflix_b200.build.build_variant(); the product is always libespflix_b200.so."""
+    override = os.environ.get("EF_LIB")
+    if override:
+        return override if os.path.isabs(override) else os.path.join(_HERE, override)
     return os.path.join(_HERE, "libespflix_b200.so")
 
 
@@ -44,6 +49,7 @@ _SIGNATURES = {
     "ef_stream_info": (_I, [_VP, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "ef_decode_picture": (_I, [_VP, _I, _VP]),
     "ef_decode_all": (_I, [_VP, _I, _VP]),
+    "ef_decode_all_to_host": (_I, [_VP, _I, _VP, _VP]),
     "ef_read_frame": (_I, [_VP, _I, _I, _VP]),
     "ef_read_frame_i420": (_I, [_VP, _I, _I, _VP]),
     "ef_write_frame_i420": (_I, [_VP, _I, _I, _VP]),
@@ -61,6 +67,8 @@ _SIGNATURES = {
     "ef_video_isr": (_I, [_VP, _I, _I, _VP]),
     "ef_blit": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I]),
     "ef_launch_count": (ctypes.c_uint64, [_VP]),
+    "ef_set_profiling": (_I, [_VP, _I]),
+    "ef_stage_ms": (_I, [_VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "ef_tsidx_scan": (_I, [_I, _VP, _VP, _I, ctypes.c_uint32, _VP, _VP, _VP]),
     "ef_tsidx_samples": (_I, [_I, _VP, _VP, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, _VP, ctypes.c_uint32, _VP]),
 }
@@ -158,6 +166,10 @@ class Context:
     def decode_all(self, n_pictures, stream=0):
         self._check(self.lib.ef_decode_all(self._h, n_pictures, stream))
 
+    def decode_all_to_host(self, n_pictures, out, stream=0):
+        """every picture of the submit to out[n_pictures][n_streams][I420] (pinned host memory; complete after sync())"""
+        self._check(self.lib.ef_decode_all_to_host(self._h, n_pictures, _ptr(out), stream))
+
     def read_frame(self, s, fb=-1):
         out = np.empty(FRAME_BYTES, dtype=np.uint8)
         self._check(self.lib.ef_read_frame(self._h, s, fb, out.ctypes.data))
@@ -249,6 +261,15 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.ef_launch_count(self._h))
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.ef_set_profiling(self._h, 1 if on else 0))
+
+    def stage_ms(self):
+        """(K0 index, K1a parse, K1b reconstruction) milliseconds of the last ef_index / ef_decode_* (synchronises)."""
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.ef_stage_ms(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
 
 
 # -- trick-mode index (indexer/indexer.cpp; SURVEY.md 8f-4) ---------------------------------------------

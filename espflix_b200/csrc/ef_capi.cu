@@ -69,6 +69,8 @@ struct DeviceScope {
 // host-visible layouts: the I420 dump and the reference's strips (video.h:36-44; player.cpp:33-46).
 // mode 0 = I420, 1 = strips. One thread per 8 bytes (8 aligned consecutive bytes never straddle a tile row:
 // luma tile rows are 16 bytes, chroma tile rows 8, and 352, 176 and 528 are multiples of 8).
+// fb_sel: 0 / 1 = that frame store; -1 = the most recent picture of each stream; -2 - p = picture p of the current
+// submit (the store flush_picture() gave it, player.cpp:692)
 __global__ void ef_export_frames_kernel(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ base_pics,
                                         const uint32_t* __restrict__ n_pics, int first, int count, int fb_sel, int mode, uint8_t* __restrict__ dst)
 {
@@ -77,7 +79,7 @@ __global__ void ef_export_frames_kernel(const uint8_t* __restrict__ frames, cons
     const uint32_t k = (uint32_t)(t / per), w = (uint32_t)(t % per);
     if (k >= (uint32_t)count) return;
     const int s = first + (int)k;
-    const int fb = fb_sel >= 0 ? fb_sel : (int)((base_pics[s] + n_pics[s]) & 1u);
+    const int fb = fb_sel >= 0 ? fb_sel : fb_sel == -1 ? (int)((base_pics[s] + n_pics[s]) & 1u) : (int)((base_pics[s] + (uint32_t)(-2 - fb_sel) + 1u) & 1u);
     const uint8_t* f = frames + ef_frame_offset(s, fb);
     const int b = (int)w * 8;
     const int src = mode == 0 ? ef_i420_to_tiled(b) : ef_strips_to_tiled(b);
@@ -99,9 +101,9 @@ __global__ void ef_reset_seq_kernel(EfDev* Dp, const uint8_t* default_intra)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D.n_streams) return;
     EfSeq* q = D.seq + (size_t)s * (D.max_seq + 1);
-    for (int n = 0; n < 128; n++) q->q_scan[n] = D.tables->qdef[n];
+    for (int n = 0; n < 128; n++) q->qz[n] = D.tables->qz[n];
     (void)default_intra;
-    q->mb_width = 22; q->mb_height = 12; q->valid = 1; q->custom = 0;
+    q->mb_width = 22; q->mb_height = 12; q->valid = 1; q->custom = 0; q->fp_rs = 0;
     D.n_pics[s] = 0; D.base_pics[s] = 0; D.n_seq[s] = 0;
 }
 
@@ -140,6 +142,9 @@ struct ef_ctx {
     bool indexed = false, submitted = false, video = false;
     uint64_t launches = 0;
     uint64_t es_bytes = 0;
+    bool profiling = false;                       // ef_set_profiling: CUDA events around K0 / K1a / K1b
+    cudaEvent_t ev_prof[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    bool prof_index = false, prof_decode = false;
 };
 
 namespace {
@@ -303,6 +308,7 @@ void ef_destroy(ef_ctx* c)
         if (c->ev_buf_free[b]) cudaEventDestroy(c->ev_buf_free[b]);
         if (c->ev_down_done[b]) cudaEventDestroy(c->ev_down_done[b]);
     }
+    for (int i = 0; i < 5; i++) if (c->ev_prof[i]) cudaEventDestroy(c->ev_prof[i]);
     if (c->ev_user) cudaEventDestroy(c->ev_user);
     if (c->ev_export) cudaEventDestroy(c->ev_export);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
@@ -400,6 +406,7 @@ int ef_index(ef_ctx* c, void* stream)
         c->active = c->pending; c->pending = -1;
         c->d = c->dd[c->active];
     }                                            // else: index the front buffer again (same input, next GOP period)
+    if (c->profiling) { CK(cudaEventRecord(c->ev_prof[0], st)); c->prof_index = true; }
     CK(cudaMemsetAsync(c->h.info, 0, 32, st));
     ef_scan_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(c->d);
     CK(cudaGetLastError());
@@ -409,6 +416,7 @@ int ef_index(ef_ctx* c, void* stream)
     ef_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->d);
     CK(cudaGetLastError());
     c->launches += 3;
+    if (c->profiling) CK(cudaEventRecord(c->ev_prof[1], st));
     CK(cudaEventRecord(c->ev_buf_free[c->active], st));
     c->indexed = true;
     return EF_OK;
@@ -447,15 +455,49 @@ int ef_stream_info(ef_ctx* c, int stream_index, int* n_pictures, int* base_pictu
     return EF_OK;
 }
 
-// K1a over picture indices [p0, p0 + k), then K1b once per picture index
-static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st)
+// staging buffer k (of two) for batched read-back, grown on demand
+static int ensure_stage2(ef_ctx* c, int k, size_t bytes)
+{
+    if (c->stage2_bytes[k] >= bytes) return EF_OK;
+    CK(cudaEventSynchronize(c->ev_down_done[k]));
+    void* v = nullptr;
+    CK(cudaMalloc(&v, bytes));
+    c->allocs.push_back(v);
+    c->d_stage2[k] = (uint8_t*)v; c->stage2_bytes[k] = bytes;
+    return EF_OK;
+}
+
+// K1a over picture indices [p0, p0 + k), then K1b once per picture index. host_dst != nullptr: every picture index
+// is exported (I420) straight after its K1b launch and copied to host_dst[p][stream] on the read-back stream while
+// the next picture index is being rebuilt - what push_video() sees, picture by picture (video.h:49).
+static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st, uint8_t* host_dst = nullptr)
 {
     DeviceScope scope_(c ? c->cfg.device : -1);
     const size_t slots = (size_t)k * c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX;
     CK(cudaMemsetAsync(c->h.mb_info, 0, slots * 4, st));
     CK(cudaMemsetAsync(c->h.parse_cursor, 0, ((size_t)k + 1) * 4, st));
+    if (c->profiling) { CK(cudaEventRecord(c->ev_prof[2], st)); c->prof_decode = true; }
     CK(ef_launch_parse(c->d, p0, k, c->sm_count, st));
-    for (int i = 0; i < k; i++) CK(ef_launch_recon(c->d, i, c->sm_count, st));
+    if (c->profiling) CK(cudaEventRecord(c->ev_prof[3], st));
+    const size_t batch_bytes = (size_t)c->cfg.n_streams * EF_FRAME;
+    for (int i = 0; i < k; i++) {
+        CK(ef_launch_recon(c->d, i, c->sm_count, st));
+        if (host_dst) {
+            const int b = c->stage_idx ^= 1;
+            int rc = ensure_stage2(c, b, batch_bytes);
+            if (rc != EF_OK) return rc;
+            CK(cudaStreamWaitEvent(st, c->ev_down_done[b], 0));            // the previous copy out of this staging buffer has finished
+            const uint64_t threads = (uint64_t)c->cfg.n_streams * (EF_FRAME / 8);
+            ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, 0, c->cfg.n_streams, -2 - (p0 + i), 0, c->d_stage2[b]);
+            CK(cudaGetLastError());
+            c->launches++;
+            CK(cudaEventRecord(c->ev_export, st));
+            CK(cudaStreamWaitEvent(c->down_stream, c->ev_export, 0));
+            CK(cudaMemcpyAsync(host_dst + (size_t)(p0 + i) * batch_bytes, c->d_stage2[b], batch_bytes, cudaMemcpyDeviceToHost, c->down_stream));
+            CK(cudaEventRecord(c->ev_down_done[b], c->down_stream));
+        }
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev_prof[4], st));
     CK(cudaEventRecord(c->ev_buf_free[c->active], st));     // the front ES buffer is in use until here
     c->launches += 1 + (uint64_t)k;
     return EF_OK;
@@ -477,6 +519,19 @@ int ef_decode_all(ef_ctx* c, int n_pictures, void* stream)
     for (int p = 0; p < n_pictures; p += c->h.rec_pics) {
         const int k = n_pictures - p < c->h.rec_pics ? n_pictures - p : c->h.rec_pics;
         int rc = decode_range(c, p, k, (cudaStream_t)stream);
+        if (rc != EF_OK) return rc;
+    }
+    return EF_OK;
+}
+
+int ef_decode_all_to_host(ef_ctx* c, int n_pictures, uint8_t* dst, void* stream)
+{
+    if (!c || !dst) return fail(EF_EINVAL, "null argument");
+    if (!c->indexed) return fail(EF_ESTATE, "ef_decode_all_to_host before ef_index");
+    if (n_pictures < 0 || n_pictures > c->cfg.max_pictures) return fail(EF_EINVAL, "n_pictures %d out of range", n_pictures);
+    for (int p = 0; p < n_pictures; p += c->h.rec_pics) {
+        const int k = n_pictures - p < c->h.rec_pics ? n_pictures - p : c->h.rec_pics;
+        int rc = decode_range(c, p, k, (cudaStream_t)stream, dst);
         if (rc != EF_OK) return rc;
     }
     return EF_OK;
@@ -505,13 +560,7 @@ int ef_read_latest_i420_async(ef_ctx* c, int first, int count, uint8_t* dst, voi
     if (first < 0 || count < 1 || first + count > c->cfg.n_streams) return fail(EF_EINVAL, "stream range out of bounds");
     const int k = c->stage_idx ^= 1;
     const size_t bytes = (size_t)count * EF_FRAME;
-    if (c->stage2_bytes[k] < bytes) {
-        CK(cudaEventSynchronize(c->ev_down_done[k]));
-        void* v = nullptr;
-        CK(cudaMalloc(&v, bytes));
-        c->allocs.push_back(v);
-        c->d_stage2[k] = (uint8_t*)v; c->stage2_bytes[k] = bytes;
-    }
+    { int rc = ensure_stage2(c, k, bytes); if (rc != EF_OK) return rc; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaStreamWaitEvent(st, c->ev_down_done[k], 0));        // the previous copy out of this staging buffer has finished
     const uint64_t threads = (uint64_t)count * (EF_FRAME / 8);
@@ -706,6 +755,34 @@ int ef_blit(ef_ctx* c, int stream_index, int fb, uint16_t* dst, int line, int x,
 }
 
 uint64_t ef_launch_count(ef_ctx* c) { return c ? c->launches : 0; }
+
+int ef_set_profiling(ef_ctx* c, int on)
+{
+    DeviceScope scope_(c ? c->cfg.device : -1);
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (on && !c->ev_prof[0]) for (int i = 0; i < 5; i++) CK(cudaEventCreate(&c->ev_prof[i]));
+    c->profiling = on != 0;
+    c->prof_index = c->prof_decode = false;
+    return EF_OK;
+}
+
+int ef_stage_ms(ef_ctx* c, float* index_ms, float* parse_ms, float* recon_ms)
+{
+    DeviceScope scope_(c ? c->cfg.device : -1);
+    if (!c) return fail(EF_EINVAL, "null context");
+    if (!c->profiling) return fail(EF_ESTATE, "ef_stage_ms without ef_set_profiling(ctx, 1)");
+    float a = 0, b = 0, r = 0;
+    if (c->prof_index) { CK(cudaEventSynchronize(c->ev_prof[1])); CK(cudaEventElapsedTime(&a, c->ev_prof[0], c->ev_prof[1])); }
+    if (c->prof_decode) {
+        CK(cudaEventSynchronize(c->ev_prof[4]));
+        CK(cudaEventElapsedTime(&b, c->ev_prof[2], c->ev_prof[3]));
+        CK(cudaEventElapsedTime(&r, c->ev_prof[3], c->ev_prof[4]));
+    }
+    if (index_ms) *index_ms = a;
+    if (parse_ms) *parse_ms = b;
+    if (recon_ms) *recon_ms = r;
+    return EF_OK;
+}
 
 // ---- trick-mode index (indexer/indexer.cpp), stateless --------------------------------------------------
 namespace {

@@ -19,7 +19,8 @@
 //   work          [total slices]                flat per-picture slice work lists (K1a's unit of work)
 //   mb_info/mb_rec[rec_pics][n_streams][264]    macroblock records K1a -> K1b, slot = macroblock address
 //   coef          [3 x es bytes] u32            coefficient lists K1a -> K1b; the list of a slice starts at
-//                                               entry 3 x (its byte offset in `es`)
+//                                               entry 3 x (its byte offset in `es`); entry = (block << 24 |
+//                                               raster position << 18) + dequantised, AAN-prescaled value
 //   fields        [n_streams][field samples]    composite output of K2 (u16)
 #pragma once
 #include <cuda_runtime.h>
@@ -38,11 +39,14 @@
 #ifndef EF_K1A_CTAS
 #define EF_K1A_CTAS 4
 #endif
-#ifndef EF_K1A_PF_L1
-#define EF_K1A_PF_L1 0
+#ifndef EF_K1A_PF_L2
+#define EF_K1A_PF_L2 1           // K1a: prefetch.global.L2 128 bytes ahead of a slice's read position (besides the cp.async ring)
 #endif
 #ifndef EF_K1A_HDR_BATCH
-#define EF_K1A_HDR_BATCH 32      // 32 = a symbol loop runs until no lane is busy (measured best: header phases are expensive)
+#define EF_K1A_HDR_BATCH 32      // waiting lanes that end a symbol loop early; 32 = the loop runs until no lane is busy
+#endif
+#ifndef EF_K1A_LUT_BITS
+#define EF_K1A_LUT_BITS 10       // K1a: the two-symbol coefficient table is indexed by the next 2^K bits of the stream
 #endif
 #ifndef EF_K1B_WARPS
 #define EF_K1B_WARPS 7       // K1b (reconstruct): warps per CTA, CTAs per SM
@@ -62,6 +66,15 @@
 //   mv:   bits 0-3 length (sign included), 4-9 value+16                          [7][32]  u16
 //   cbp:  bits 0-3 length, 4-9 pattern, indexed by the next 9 bits               [512]    u16
 //   ptype:bits 0-2 length, 3-7 macroblock_type flags, indexed by next 6 bits     [64]     u8
+//   qz:   per scan position n: quantiser byte | AAN prescale << 8 | raster index zig_zag[n] << 18; [0..63] intra,
+//         [64..127] non-intra (the layout of a coefficient-list entry above bit 18)     [128]    u32
+//   lut2: the fast path of the coefficient parser, indexed by the next EF_K1A_LUT_BITS bits: up to two
+//         (run, level) symbols and a trailing end-of-block that lie wholly inside those bits.
+//         .x = bits consumed | run1 << 8 | (int8) level1 << 16 | span << 24, span = scan positions advanced before
+//              the last coefficient (run1, or run1 + 1 + run2); 127 = not decodable from these bits (long code,
+//              escape, invalid): the parser then decodes one symbol through `dct`
+//         .y = flags (1 first coefficient, 2 second coefficient, 4 end of block) | run2 << 8 | (int8) level2 << 16
+//         [0] = dct_coeff_next context, [1] = first coefficient of a non-intra block   [2][2^K]  u32 x 2
 struct EfTables {
     uint16_t dct[26 * 32];
     uint16_t mba[8 * 32];
@@ -70,19 +83,23 @@ struct EfTables {
     uint8_t ptype[64];
     uint8_t qdef[128];      // default quantiser matrices in SCAN order: [0..63] intra, [64..127] non-intra (all 16)
     uint16_t zp[64];        // scan position n -> zig_zag[n] | scale_dct_q[zig_zag[n]] << 8 (player.cpp:150-170)
+    uint32_t qz[128];       // default matrices in the parser's combined form (see above)
     uint8_t izz[64];        // raster index -> zig-zag scan position
     uint8_t prescale[64];   // AAN prescale, raster (reference scale_dct_q, player.cpp:161)
     uint8_t zigzag[64];     // scan position -> raster index
+    uint2 lut2[(2 << EF_K1A_LUT_BITS) > 16 ? (2 << EF_K1A_LUT_BITS) : 16];
 };
 
 // sequence state as the decode kernel reads it: quantiser matrices in SCAN order (the parser
 // dequantises symbol by symbol), with quirk Q4 already applied: entry n = the byte the reference
-// finds at raster index zigzag[n] of its stream-order copy (player.cpp:646-651, 1113).
+// finds at raster index zigzag[n] of its stream-order copy (player.cpp:646-651, 1113), in the
+// combined form of EfTables::qz (quantiser | prescale << 8 | raster index << 18).
 struct __align__(16) EfSeq {
-    uint8_t q_scan[128];     // [0..63] intra, [64..127] non-intra
+    uint32_t qz[128];        // [0..63] intra, [64..127] non-intra
     uint16_t mb_width, mb_height;
     uint16_t valid, custom;  // custom = a matrix was loaded from the stream (else K1 uses the shared-memory defaults)
-    uint32_t pad1[2];
+    uint32_t fp_rs;          // full_pel_forward | forward_r_size << 1 of the last P picture header (decoder members in the reference: a B/D picture at the start of the next submit is parsed with them)
+    uint32_t pad1;
 };
 
 struct __align__(16) EfPic {

@@ -105,6 +105,100 @@ __device__ __forceinline__ uint4 blit_quad(uint32_t y4, uint32_t dither, uint32_
                       ((p1 << 16) | (p0 >> 8)) + cb, (((p1 << 8) & 0xFF000000u) | (p0 >> 16)) + (cb << 8));
 }
 
+#ifndef EF_K2_LEGACY
+// ---- K2 v5: a CTA synthesises a BAND of 16 consecutive lines of one stream in shared memory and hands every
+// finished line to the TMA engine (cp.async.bulk.global.shared::cta): the field leaves the SM as 1,824-byte
+// (PAL 2,272-byte) bulk stores instead of 16-byte STG, which took the output off the L1/TEX pipe - the v4 kernel
+// was bound there (86 % busy at 42 % DRAM throughput, profiles/r01_k2_details.txt). Bands coincide with
+// macroblock rows of the tiled frame (the active area starts at line 32 / 64), so the loads can follow the
+// tile layout: a warp takes two 8-pixel groups x 16 rows = 256 contiguous luma bytes and 2 x 64 contiguous chroma
+// bytes of ONE tile (2 + 1 + 1 L1 wavefronts instead of 8 + 8 + 8 when its lanes ran along a scan line).
+// Shared-memory lines are padded by 16 bytes: the 16-byte stores of 8 consecutive rows then hit 32 distinct banks.
+// grid: x = band (17 NTSC / 20 PAL), y = stream; 352 threads = 11 warps x 2 tile columns = the 22 macroblocks of a row.
+constexpr int kK2Threads = 352;
+
+__device__ __forceinline__ void bulk_store_line(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+template <bool kNtsc>
+__global__ void __launch_bounds__(kK2Threads)
+ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter, const EfPresent pr)
+{
+    using G = Geo<kNtsc>;
+    constexpr int CPL = G::W / 8;                                          // 16-byte chunks per line
+    constexpr int LB = G::W * 2, LS = LB + 16;                             // bytes per line in the field / in shared memory
+    constexpr int BLIT_C = G::BLIT / 8, BLIT_N = 2 * EF_W / 8;             // the blit span in chunks: [BLIT_C, BLIT_C + 88)
+    __shared__ __align__(128) uint8_t sm[16 * LS];
+    const EfDev& D = *Dp;
+    const uint32_t* tab = D.color_tab;                                     // 3 KB chroma LUT through L1
+    const int stream = (int)blockIdx.y;
+    const int line0 = (int)blockIdx.x * 16;
+    const int nlines = min(16, G::LINES - line0);
+    const int fl0 = line0 - G::TOP;                                        // frame line of the band's first line (bands = macroblock rows)
+    const bool active = fl0 >= 0 && fl0 < EF_H && fb_sel != -2;            // -2: no frame presented yet (video.cpp:1140)
+
+    // sync, burst, black level, vertical sync, overlay: every chunk outside the blit span
+    const int per_line = active ? CPL - BLIT_N : CPL;
+    for (int i = (int)threadIdx.x; i < per_line * nlines; i += kK2Threads) {
+        const int l = i / per_line, k = i - l * per_line;
+        const int c = (active && k >= BLIT_C) ? k + BLIT_N : k;
+        *(uint4*)(sm + l * LS + c * 16) = blank_chunk<kNtsc>(D, pr, line0 + l, c * 8);
+    }
+
+    if (active) {
+        const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
+        const int row = lane & 15, fl = fl0 + row;                         // frame line 0..191
+        int fb0 = fb_sel >= 0 ? fb_sel : (int)((D.base_pics[stream] + D.n_pics[stream]) & 1u);
+        // two-frame horizontal scroll (video.cpp:1146-1154): blit(f, dst, i, h, 352-h) then blit(f^1, dst + (352-h)*2, i, 0, h)
+        int h = pr.hscroll;
+        if (h < 0) { h += EF_W; fb0 ^= 1; }
+        const int split = (EF_W - h) >> 3;                                 // first 8-pixel group drawn by the second blit
+        const uint32_t dither = c_dither[(fl & 3) + ((frame_counter & 1) << 2)];
+        const int cy = fl >> 1, ncy = cy + (fl == 191 ? 0 : 1);            // odd lines average with the next chroma row (video.cpp:704-716)
+        const int yoff = (fl >> 4) * EF_MBW_MAX * EF_TILE + (fl & 15) * 16;
+        const int coff = (cy >> 3) * EF_MBW_MAX * EF_TILE + (cy & 7) * 8 + 256;      // get_cr(line>>1); get_cb is the next 64-byte plane
+        const int noff = (ncy >> 3) * EF_MBW_MAX * EF_TILE + (ncy & 7) * 8 + 256;
+        const int vt = (fl & 1) ? 512 : 256;
+        for (int gd = warp * 2 + (lane >> 4); gd < 2 * EF_W / 16; gd += (kK2Threads / 32) * 2) {   // destination group 0..43
+            const bool second = gd >= split;
+            const int g = second ? gd - split : gd + (h >> 3);             // 8-pixel group of the source frame
+            const bool call_start = second ? g == 0 : gd == 0;             // blit() starts its luma carry at 0
+            const uint8_t* f = D.frames + ef_frame_offset(stream, fb0 ^ (int)second);
+            const int tcol = (g >> 1) * EF_TILE, sub = g & 1;
+            uint32_t u4 = *(const uint32_t*)(f + coff + tcol + sub * 4);
+            uint32_t v4 = *(const uint32_t*)(f + coff + tcol + sub * 4 + 64);
+            if (fl & 1) {
+                u4 = ((u4 >> 1) & 0x7F7F7F7Fu) + ((*(const uint32_t*)(f + noff + tcol + sub * 4) >> 1) & 0x7F7F7F7Fu);
+                v4 = ((v4 >> 1) & 0x7F7F7F7Fu) + ((*(const uint32_t*)(f + noff + tcol + sub * 4 + 64) >> 1) & 0x7F7F7F7Fu);
+            }
+            const uint2 y8 = *(const uint2*)(f + yoff + tcol + sub * 8);
+            uint32_t lum = 0;                                              // carry = last pixel of the previous group, 0 at the start of a blit() call
+            if (!call_start) {
+                const int q = 2 * g - 1;                                   // previous 4-pixel group
+                lum = ((((*(const uint32_t*)(f + yoff + (q >> 2) * EF_TILE + (q & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
+            }
+            const uint4 o0 = blit_quad(y8.x, dither, chroma_word(tab, u4, v4, vt), chroma_word(tab, u4 >> 8, v4 >> 8, vt), lum);
+            const uint4 o1 = blit_quad(y8.y, dither, chroma_word(tab, u4 >> 16, v4 >> 16, vt), chroma_word(tab, u4 >> 24, v4 >> 24, vt), lum);
+            uint8_t* o = sm + row * LS + (G::BLIT + gd * 16) * 2;
+            *(uint4*)o = o0;
+            *(uint4*)(o + 16) = o1;
+        }
+    }
+
+    // generic-proxy writes -> async proxy, then one bulk store per line (the field rows of a band are contiguous in HBM)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if ((int)threadIdx.x < nlines) {
+        uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)(line0 + (int)threadIdx.x) * G::W;
+        bulk_store_line(out, sm + (int)threadIdx.x * LS, LB);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory must stay valid until the engine has read it
+    }
+}
+#else
 // grid: x = threads of one field / 256, y = stream. One thread = two adjacent 16-byte chunks (32 bytes out,
 // 8 luma pixels in: one 8-byte luma load, one 4-byte load per chroma plane). The pairing is phased so that
 // the blit span starts on a pair boundary (NTSC chunk 20: pairs (2j, 2j+1); PAL chunk 35: pairs (2j-1, 2j)).
@@ -184,6 +278,8 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter,
     }
 }
 
+#endif
+
 // single blit() call into a device buffer (line-blit entry point; used by ef_blit): one thread per 4 luma pixels
 __global__ void ef_blit_kernel(const EfDev* __restrict__ Dp, int stream, int fb, int fl, int x, int width, int frame_counter, uint16_t* __restrict__ dst)
 {
@@ -227,6 +323,12 @@ __global__ void ef_blit_kernel(const EfDev* __restrict__ Dp, int stream, int fb,
 
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream)
 {
+#ifndef EF_K2_LEGACY
+    const dim3 bands((unsigned)(g.line_count + 15) / 16, (unsigned)n_streams);
+    if (g.ntsc) ef_composite_kernel<true><<<bands, kK2Threads, 0, stream>>>(dev, fb, frame_counter, pr);
+    else ef_composite_kernel<false><<<bands, kK2Threads, 0, stream>>>(dev, fb, frame_counter, pr);
+    return cudaGetLastError();
+#else
     const unsigned items = (unsigned)(g.line_width >> 4) + (((unsigned)g.blit_start >> 3) & 1u);   // 32-byte work items per line (see the kernel)
     const unsigned groups = (items + 15) / 16;
     const unsigned threads = groups * 32 * (unsigned)(g.line_count / 2);   // both standards have an even line count
@@ -234,6 +336,7 @@ cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometr
     if (g.ntsc) ef_composite_kernel<true><<<grid, 256, 0, stream>>>(dev, fb, frame_counter, pr);
     else ef_composite_kernel<false><<<grid, 256, 0, stream>>>(dev, fb, frame_counter, pr);
     return cudaGetLastError();
+#endif
 }
 
 cudaError_t ef_launch_blit(const EfDev* dev, int stream_index, int fb, int line, int x, int width, int frame_counter, uint16_t* dst, cudaStream_t stream)

@@ -34,6 +34,7 @@
 // Q5 single-coefficient blocks bypass the IDCT with floor; Q6 first macroblock of a slice lands in
 // column 0; Q7 intra DC-only blocks are replicated unclamped.
 #include "ef_common.cuh"
+#include "ef_coef_step.cuh"
 
 namespace {
 
@@ -59,8 +60,12 @@ struct SharedTables {                           // same layout as the head of Ef
     uint8_t ptype[64];
     uint8_t qdef[128];
     uint16_t zp[64];                            // scan position -> raster index | AAN prescale << 8
+    uint32_t qz[128];                           // default matrices: quantiser | prescale << 8 | raster index << 18
 };
 constexpr int kTableBytes = (sizeof(SharedTables) + 15) & ~15;
+constexpr int kLutBits = EF_K1A_LUT_BITS;       // the two-symbol table (EfTables::lut2) is indexed by the next kLutBits bits
+constexpr int kLutSize = 1 << kLutBits;         // entries per context
+constexpr int kLutBytes = kLutBits > 0 ? 2 * kLutSize * (int)sizeof(uint2) : 0;
 
 // ---------------------------------------------------------------------------------------------
 // bit reader (FILL_BITS/peek_bits/get_bits, player.cpp:348-352, 495-514): MSB-first. `hi` holds the
@@ -108,7 +113,9 @@ struct BitReader {
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(sring + (rp & 7u) * kRingStride) : "memory");
             lo = __byte_perm(raw, 0, 0x0123);
             copy_in(rp + 7);                                              // into the slot that was read one refill ago
+#if EF_K1A_PF_L2
             if ((rp & 7u) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + rp + 32));   // 128 bytes ahead of this slice's read position
+#endif
             rp++;
         }
     }
@@ -125,7 +132,7 @@ struct SliceState {
     BitReader br;
     uint32_t* wptr;          // coefficient list of the macroblock in flight (HBM); entries are stored at wptr[cnt]
     uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture | destination frame store << 31
-    const uint8_t* qtab;     // scan-order quantiser tables [intra 64 | non-intra 64]: the shared-memory defaults or the stream's own in HBM
+    const uint32_t* qz;      // scan-order quantiser | prescale | raster index tables [intra 64 | non-intra 64] in global memory: the defaults (EfTables::qz, L1 resident) or the stream's own
     int mbw, mbh;
     int mb_x, mb_y;          // last macroblock handled
     int first;               // next macroblock is the first of the slice (Q6)
@@ -184,18 +191,6 @@ __device__ __forceinline__ void idct8(int (&v)[8])
     v[0] = b7 + y4; v[1] = x4 + y3; v[2] = y5 - x0; v[3] = y6 - y7;
     v[4] = y6 + y7; v[5] = x0 + y5; v[6] = y3 - x4; v[7] = y4 - b7;
     // kFinal: the outputs are left scaled by 256 (the reference's final >> 8 is folded into pin4)
-}
-
-// dequantise one level given as magnitude + sign (block(), player.cpp:1110-1119): v = 2*level (+-1 when
-// not intra; +1 for level 0); v = (v * qscale * q) / 16 with C truncation, i.e. on the magnitude; oddify
-// towards zero, except that 0 becomes +1 whatever the sign was (Q2); clamp to [-2048, 2047].
-__device__ __forceinline__ int dequant(int mag, int neg, int intra, int qsq)
-{
-    int m = ((2 * mag + (intra ? 0 : 1)) * qsq) >> 4;
-    if (m == 0) neg = 0;
-    m = (max(m, 1) - 1) | 1;
-    m = min(m, 2047 + neg);
-    return neg ? -m : m;
 }
 
 __device__ __forceinline__ uint32_t pin4(uint32_t pred, int r0, int r1, int r2, int r3)
@@ -441,19 +436,23 @@ __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
 //
 // Lane states: no slice (idle / exhausted), WAITING for the header of its next macroblock, BUSY in the
 // coefficient state machine. Header phases (flush finished records, refill idle lanes, parse headers)
-// alternate with symbol loops (one VLC symbol per busy lane per step); a symbol loop ends when no lane is
-// busy or when kHdrBatch lanes are waiting - lanes do not wait for the slowest macroblock of the warp.
+// alternate with symbol loops (per busy lane and step: up to two coefficients and an end of block from one
+// table look-up); a symbol loop ends when no lane is busy or when kHdrBatch lanes are waiting.
 // =================================================================================================
 __global__ void __launch_bounds__(kParseThreads, kParseCtasPerSm)
 ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
 {
-    __shared__ __align__(16) uint8_t smem[kTableBytes + kRingBytes];
+    extern __shared__ __align__(16) uint8_t smem[];           // tables | two-symbol table | bitstream rings
     SharedTables& T = *(SharedTables*)smem;
+    const uint2* lut = (const uint2*)(smem + kTableBytes);
     const EfDev& D = *Dp;
     {   // stage the tables (the first sizeof(SharedTables) bytes of EfTables have the same layout)
         const uint32_t* src = (const uint32_t*)D.tables;
         uint32_t* dst = (uint32_t*)smem;
         for (int i = threadIdx.x; i < (int)(sizeof(SharedTables) / 4); i += blockDim.x) dst[i] = src[i];
+        const uint4* lsrc = (const uint4*)D.tables->lut2;
+        uint4* ldst = (uint4*)(smem + kTableBytes);
+        for (int i = threadIdx.x; i < kLutBytes / 16; i += blockDim.x) ldst[i] = lsrc[i];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -465,14 +464,22 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
     const uint32_t n_slots = (uint32_t)D.n_streams * (EF_MBW_MAX * EF_MBH_MAX);
 
     SliceState s;
-    s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qtab = T.qdef; s.mbw = 0; s.mb_x = s.mb_y = 0;
-    s.br.sring = smem_u32(smem + kTableBytes) + threadIdx.x * 4;
+    s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qz = D.tables->qz; s.mbw = 0; s.mb_x = s.mb_y = 0;
+    s.br.sring = smem_u32(smem + kTableBytes + kLutBytes) + threadIdx.x * 4;
     bool active = false, exhausted = false, busy = false;
     // the macroblock in flight: info word under construction (bit 0 set = a record is owed), entry count |
     // skip run << 16, motion vector, record slot
     uint32_t info_acc = 0, cnt = 0, skipw = 0, mvw = 0, slot = 0;
     uint32_t blk24 = 0, blkbit = 0;                           // current block: number << 24, 0x100 << number
-    int cbp_rem = 0, n = -1, intra = 0;                       // n < 0: the next symbol starts a block
+    int cbp_rem = 0, n = 0, intra = 0, ctx = 0;               // n = scan position of the block in flight; ctx = 1: the next symbol is the first coefficient of a non-intra block
+    // next coded block of the macroblock in flight (cbp_rem != 0): block number, contexts, intra DC
+    auto start_block = [&]() {
+        const int blk = __ffs(cbp_rem) - 1;
+        blk24 = (uint32_t)blk << 24; blkbit = 0x100u << blk;
+        cbp_rem &= cbp_rem - 1;
+        n = 0; ctx = 1;                                       // dct_coeff_first: no end of block, '1s' = (0, 1)
+        if (intra) { D.mb_rec[slot].dc[blk] = parse_dc(s, blk); n = 1; ctx = 0; }
+    };
     // first round: thread t takes slice t; afterwards lanes whose slice ended pull from the cursor
     const uint32_t first_round = gridDim.x * blockDim.x;
     bool first_fill = true;
@@ -510,7 +517,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                         const EfSeq* seq = D.seq + (size_t)w.stream * (D.max_seq + 1) + (w.info >> 16);
                         s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
                         s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
-                        s.qtab = seq->custom ? (const uint8_t*)seq->q_scan : (const uint8_t*)T.qdef;
+                        s.qz = seq->custom ? (const uint32_t*)seq->qz : (const uint32_t*)D.tables->qz;
                         const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
                         s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
                         s.slot_base |= ((D.base_pics[w.stream] + w.pic + 1u) & 1u) << 31;      // destination frame store: flush_picture(), player.cpp:692
@@ -532,67 +539,45 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                     slot = (s.slot_base & 0x7FFFFFFFu) + (uint32_t)(s.mb_y * EF_MBW_MAX + s.mb_x);
                     info_acc = 1u | ((uint32_t)intra << 1) | ((uint32_t)cbp_rem << 2);
                     cnt = 0;
-                    n = -1;
                     busy = cbp_rem != 0;
+                    if (busy) start_block();
                 } else active = false;
             }
         } while (__any_sync(0xFFFFFFFFu, !active && !exhausted));
         if (!__any_sync(0xFFFFFFFFu, active)) break;
 
-        // ---- symbol loop: one VLC symbol per busy lane per step -----------------------------------------
-        const uint8_t* qrow = s.qtab + (intra ? 0 : 64);
+        // ---- symbol loop: per busy lane and step, up to two coefficients and an end of block -------------
+        // Fast path: the next kLutBits bits index the two-symbol table; everything that lies wholly inside them
+        // (one or two run/level codes with their sign bits, a closing '10') is taken in one step. Long codes,
+        // the escape, invalid prefixes and symbols that would run past scan position 63 decode one symbol
+        // through the clz-indexed table (and fold a following end of block in).
+        const uint32_t* qrow = s.qz + (intra ? 0 : 64);
+        const int kq = intra ? 0 : 1;
         for (;;) {
             const unsigned bmask = __ballot_sync(0xFFFFFFFFu, busy);
             if (!bmask) break;
             if (kHdrBatch < 32 && __popc(__ballot_sync(0xFFFFFFFFu, active && !busy)) >= kHdrBatch) break;
             if (busy) {
                 BitReader& br = s.br;
-                if (n < 0) {                                   // next coded block of this macroblock
-                    const int blk = __ffs(cbp_rem) - 1;
-                    blk24 = (uint32_t)blk << 24; blkbit = 0x100u << blk;
-                    cbp_rem &= cbp_rem - 1;
-                    n = 0;
-                    if (intra) { D.mb_rec[slot].dc[blk] = parse_dc(s, blk); n = 1; }
-                }
-                const uint32_t bits = br.peek();
-                const int lz = min(__clz(bits), 12);               // row 12 / 25 = not a code
-                // index = row * 32 + the five bits after the leading one; (bits << lz) >> 26 is "1xxxxx" = 32 + those bits
-                const int ctx = n == 0 ? 13 * 32 - 32 : -32;       // first-coefficient context lives in rows 13..25
-                const uint32_t e = T.dct[ctx + lz * 32 + (int)((bits << lz) >> 26)];
-                int len = e & 31, run = (e >> 5) & 31, mag = (int)(e >> 10);     // mag = |level|
-                int neg = (int)((bits >> ((32 - len) & 31)) & 1);                      // sign = last bit of a regular code
-                bool end_block = false, derail = false;
-                if (!mag) {
-                    if (len == 2) {                            // '10': end of block (player.cpp:1075)
-                        end_block = true;
-                        if (n == 1) info_acc |= blkbit;        // Q5
-                    } else if (run == 1) {                     // escape: 6-bit run, 8- or 16-bit level (player.cpp:1092)
-                        run = (int)((bits >> 20) & 63);
-                        const int b = (int)((bits >> 12) & 255);
-                        int level;
-                        if (b == 0) { level = (int)((bits >> 4) & 255); len = 28; }
-                        else if (b == 128) { level = (int)((bits >> 4) & 255) - 256; len = 28; }
-                        else { level = (int)(int8_t)b; len = 20; }
-                        mag = abs(level); neg = level < 0;
-                    } else derail = true;                      // not a code: the reference derails here
-                }
-                if (derail) {                                  // give up on this and the remaining blocks, end the slice
+                const uint32_t w = br.peek();
+                const EfCoefStep st = ef_coef_step(w, ctx != 0, n, lut, T.dct);
+                const uint32_t fl = st.fl;
+                const int len = st.len;
+                ctx = 0;
+                if (fl & EF_STEP_COEF1) { n += st.run1; s.wptr[cnt++] = ef_coef_entry(__ldg(qrow + n), st.lvl1, s.qscale, kq, blk24); n++; }
+                if (fl & EF_STEP_COEF2) { n += st.run2; s.wptr[cnt++] = ef_coef_entry(__ldg(qrow + n), st.lvl2, s.qscale, kq, blk24); n++; }
+                if (fl & 16u) {                                // give up on this and the remaining blocks, end the slice
                     info_acc |= (blkbit << 6) | ((uint32_t)cbp_rem << 14);
                     s.mb_y = s.mbh;
                     busy = false;
                 } else {
                     br.skip(len);
-                    if (!end_block) {
-                        n += run;
-                        if (n >= 64) { info_acc |= blkbit << 6; end_block = true; }     // block() returns -1: nothing is stored
-                        else {
-                            const int v = dequant(mag, neg, intra, s.qscale * (int)qrow[n]);
-                            const uint32_t zp = T.zp[n];                                   // zz = zig_zag[n]; b[zz] = v * scale_dct_q[zz] (player.cpp:1108, 1121)
-                            s.wptr[cnt++] = ((uint32_t)(v * (int)(zp >> 8)) & 0x3FFFFu) | ((zp & 63u) << 18) | blk24;
-                            n++;
-                        }
+                    if (fl & 12u) {
+                        if (fl & 8u) info_acc |= blkbit << 6;
+                        else if (n == 1) info_acc |= blkbit;   // Q5
+                        busy = cbp_rem != 0;
+                        if (busy) start_block();
                     }
-                    if (end_block) { n = -1; busy = cbp_rem != 0; }
                 }
             }
         }
@@ -712,7 +697,8 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
         }
 
         // expand the coefficient list into the dense scratch (entries of aborted blocks are dropped)
-#define EF_EXPAND(ent) { const int eb = ((ent) >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + (((ent) >> 18) & 63)] = ((int)((ent) << 14)) >> 14; }
+        // entry = (block << 24 | raster position << 18) + value, |value| < 2^17: adding 2^17 undoes the borrow of a negative value
+#define EF_EXPAND(ent) { const uint32_t hi_ = (ent) + 0x20000u; const int eb = (hi_ >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((hi_ >> 18) & 63)] = ((int)((ent) << 14)) >> 14; }
         if (hl < entries) EF_EXPAND(e0)
         if (hl + 16 < entries) EF_EXPAND(e1)
         if (hl + 32 < entries) EF_EXPAND(e2)
@@ -803,6 +789,7 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
 
 // host-side launch helpers -----------------------------------------------------------------------
 size_t ef_recon_smem_bytes() { return (size_t)kReconWarps * kWarpBytes; }
+static constexpr size_t kParseSmemBytes = (size_t)kTableBytes + kLutBytes + kRingBytes;
 
 static int g_parse_ctas = kParseCtasPerSm, g_recon_ctas = kReconCtasPerSm;   // resident CTAs per SM, measured by the occupancy API
 
@@ -817,7 +804,9 @@ cudaError_t ef_decode_configure()
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ef_recon_kernel, kReconWarps * 32, ef_recon_smem_bytes());
     if (e != cudaSuccess) return e;
     if (n >= 1) g_recon_ctas = n;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ef_parse_kernel, kParseThreads, 0);
+    e = cudaFuncSetAttribute(ef_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kParseSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ef_parse_kernel, kParseThreads, kParseSmemBytes);
     if (e != cudaSuccess) return e;
     if (n >= 1) g_parse_ctas = n;
     return cudaSuccess;
@@ -828,7 +817,7 @@ int ef_decode_resident_ctas(int which) { return which == 0 ? g_parse_ctas : g_re
 // parse every slice of picture indices [pic0, pic0 + n_pics) into record pictures 0 .. n_pics-1
 cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream)
 {
-    ef_parse_kernel<<<sm_count * g_parse_ctas, kParseThreads, 0, stream>>>(dev, pic0, n_pics);
+    ef_parse_kernel<<<sm_count * g_parse_ctas, kParseThreads, kParseSmemBytes, stream>>>(dev, pic0, n_pics);
     return cudaGetLastError();
 }
 

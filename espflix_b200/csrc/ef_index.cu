@@ -50,7 +50,10 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
     uint32_t* soff = D.slice_off + (size_t)s * D.max_slices;
     uint8_t* scode = D.slice_code + (size_t)s * D.max_slices;
 
-    // roll the state of the previous submit: ping-pong phase and the last sequence header
+    // roll the state of the previous submit: ping-pong phase, the last sequence header and the forward-vector
+    // parameters of the last P picture header (decoder members in the reference, player.cpp:716-722)
+    uint32_t fp_rs = seqs[0].fp_rs;
+    __syncwarp();
     {
         const uint32_t prev_seq = min(D.n_seq[s], (uint32_t)D.max_seq);
         if (prev_seq) {
@@ -69,7 +72,7 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
     const uint64_t span = len + misalign;
 
     uint32_t n_pic = 0, n_slice = 0, n_seq = 0;           // warp-uniform running counts
-    uint32_t fp_rs = 0;                                   // full_pel | r_size << 1 of the last P header (stale state a B/D picture would see)
+    // fp_rs: full_pel | r_size << 1 of the last P header (stale state a B/D picture would see)
     bool stop = false;
 
     // the sweep is latency bound (one warp per stream): keep the loads of the next two 512-byte chunks in flight
@@ -145,8 +148,9 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
                             const int zz = D.tables->zigzag[n];
                             const uint32_t qi = load_intra ? bits_at(es, len, hb + 63 + 8 * zz, 8) : c_default_intra_q[zz];
                             const uint32_t qn = load_inter ? bits_at(es, len, after_intra + 1 + 8 * zz, 8) : 16u;
-                            q->q_scan[n] = (uint8_t)qi;
-                            q->q_scan[64 + n] = (uint8_t)qn;
+                            const uint32_t hi = ((uint32_t)D.tables->prescale[zz] << 8) | ((uint32_t)zz << 18);     // EfTables::qz form
+                            q->qz[n] = (qi & 255u) | hi;
+                            q->qz[64 + n] = (qn & 255u) | hi;
                         }
                         if (lane == 0) {
                             q->mb_width = (uint16_t)((hsize + 15) >> 4);
@@ -172,6 +176,8 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
         pics[i].n_slices = next - first;
     }
     if (lane == 0) {
+        seqs[0].fp_rs = fp_rs;                                  // both the carried entry and the one the next submit rolls into it
+        seqs[min(n_seq, (uint32_t)D.max_seq)].fp_rs = fp_rs;
         D.n_pics[s] = np;
         D.n_seq[s] = n_seq;
         atomicMax(&D.info[0], np);

@@ -27,6 +27,7 @@
  *   ef_decode_all                 the for(;;) of MpegDecoder::run() player.cpp:1355 over one submit: every
  *                                 slice of every picture is parsed in ONE launch, then one reconstruction
  *                                 launch per picture index
+ *   ef_decode_all_to_host         the same loop with the push_video() hand-over of every picture (video.h:49)
  *   ef_read_frame / _i420         what push_video(Frame*,front,pts,mode) video.h:49 hands to the
  *                                 display side: the striped Frame (video.h:36-44) of one stream
  *   ef_video_init                 video_init(int ntsc) video.cpp:572
@@ -107,6 +108,11 @@ int ef_decode_picture(ef_ctx* ctx, int pic, void* stream);
 /* All pictures 0..n_pictures-1 of the submit on `stream`: K1a parses every slice of all of them in ONE launch
  * (parsing needs no pixels), then K1b runs once per picture index. Prefer this over a loop of ef_decode_picture. */
 int ef_decode_all(ef_ctx* ctx, int n_pictures, void* stream);
+/* The same, handing EVERY picture to the host the way the reference's decoder hands every picture to push_video()
+ * (video.h:49; player.cpp:692-702): after the K1b launch of picture index p the batch is exported as I420 and copied
+ * to dst[p][stream] (n_pictures x n_streams x EF_I420_BYTES, should be pinned) on the context's read-back stream
+ * while picture index p + 1 is rebuilt. Complete after ef_sync. Streams with fewer pictures repeat stale data. */
+int ef_decode_all_to_host(ef_ctx* ctx, int n_pictures, uint8_t* dst, void* stream);
 
 /* Frame stores. fb = 0/1 is the reference's _fb[] index; -1 = the frame holding the most recently
  * decoded picture of that stream (what the next push_video would present). Synchronous. */
@@ -148,6 +154,11 @@ int ef_blit(ef_ctx* ctx, int stream_index, int fb, uint16_t* dst, int line, int 
 
 /* Launch counter: kernels this library has launched since ef_create (bench.py "gpu_launches"). */
 uint64_t ef_launch_count(ef_ctx* ctx);
+/* Stage timing, the counterpart of the reference's MEASURE() tick counters (player.cpp:1001, streamer.h): with
+ * profiling on, ef_index and ef_decode_* bracket K0, K1a and the K1b launches with CUDA events on the caller's
+ * stream; ef_stage_ms waits for and returns the durations of the LAST ef_index / last ef_decode_* range. */
+int ef_set_profiling(ef_ctx* ctx, int on);
+int ef_stage_ms(ef_ctx* ctx, float* index_ms, float* parse_ms, float* recon_ms);
 
 /* ---- trick-mode index: the reference's offline tool, indexer/indexer.cpp -------------------
  * Stateless (no context); host buffers; the scans run on `device`.

@@ -228,3 +228,91 @@ def test_full_baseline_batch_is_bit_exact(oracle):
     g = got.reshape(len(streams) // d, d, -1)
     assert np.array_equal(g, np.broadcast_to(g[0], g.shape)), "a replica differs from its original"
     ctx.close()
+
+
+def _start_codes(es):
+    e = np.asarray(es)
+    hits = np.nonzero((e[:-3] == 0) & (e[1:-2] == 0) & (e[2:-1] == 1))[0]
+    return [(int(p), int(e[p + 3])) for p in hits]
+
+
+def test_truncated_slice_does_not_disturb_its_neighbours(oracle):
+    """Damaged input (a lost TS packet, a cut file): a slice that ends in the middle of a block is followed at once
+    by the next stream's start code and payload, i.e. by non-zero bytes in coefficient context. The parser has
+    to derail on the 23 zero bits of the start code prefix (>= 12 leading zeros is not a code) instead of decoding
+    stale bytes as coefficients: the neighbours' coefficient lists, records and pictures must stay intact, and
+    so must the pictures of the damaged stream before the cut."""
+    full = [synth.generate(synth.SEED0 + 400 + i)[0] for i in range(5)]
+    streams = [np.asarray(f).copy() for f in full]
+    cuts = {}
+    for i, frac in ((0, 0.4), (2, 0.7), (4, 0.15)):
+        sc = [p for p, c in _start_codes(full[i]) if 1 <= c <= 0xAF]
+        last = sc[-1]                                                   # last slice of the last picture
+        cut = last + 4 + max(3, int((len(full[i]) - last - 4) * frac))
+        streams[i] = np.asarray(full[i][:cut]).copy()
+        cuts[i] = cut
+    ctx = espflix_b200.Context(n_streams=len(streams), max_pictures=12, es_capacity=sum(len(s) for s in streams) + 4096, fields=False)
+    blob, off = ctx.pack(streams)
+    for _ in range(2):                                                  # twice: the second pass runs over a used list buffer
+        ctx.submit_es(blob, off)
+        ctx.index()
+        ctx.decode_all(12)
+        got = ctx.read_latest_i420()
+        for i, f in enumerate(full):
+            want = oracle.decode_es(f)
+            base = ctx.stream_info(i)[1]
+            prev = ctx.read_frame_i420(i, ((base + 12) & 1) ^ 1)
+            assert np.array_equal(prev, want[10]), "stream %d picture 10: %s" % (i, _first_diff(prev, want[10]))
+            if i not in cuts:
+                assert np.array_equal(got[i], want[11]), "intact stream %d: %s" % (i, _first_diff(got[i], want[11]))
+            else:                                                       # rows above the damaged slice are intact
+                rows = 16 * 11
+                assert np.array_equal(got[i][: 352 * rows], want[11][: 352 * rows]), "stream %d rows above the cut slice" % i
+        ctx.reset()
+    ctx.close()
+
+
+def test_decode_all_to_host_hands_over_every_picture(oracle):
+    """ef_decode_all_to_host = the decode loop with the reference's push_video() hand-over: every picture of every
+    stream arrives on the host, exported between the reconstruction launches while the next picture is rebuilt
+    (the two frame stores of a stream are overwritten two pictures later). Two submits in a row exercise the
+    alternating staging buffers and the carried ping-pong phase."""
+    n, pics = 7, 9
+    batches = [[synth.generate(synth.SEED0 + 600 + 10 * b + i, n_pictures=pics, gop=pics)[0] for i in range(n)] for b in range(2)]
+    ctx = espflix_b200.Context(n_streams=n, max_pictures=pics, es_capacity=1 << 22, fields=False)
+    for b, streams in enumerate(batches):
+        out = np.zeros((pics, n, 101376), dtype=np.uint8)
+        blob, off = ctx.pack(streams)
+        ctx.submit_es(blob, off)
+        ctx.index()
+        ctx.decode_all_to_host(pics, out)
+        ctx.sync()
+        for i, es in enumerate(streams):
+            want = oracle.decode_es(es)
+            for p in range(pics):
+                assert np.array_equal(out[p, i], want[p]), "batch %d stream %d picture %d: %s" % (b, i, p, _first_diff(out[p, i], want[p]))
+    ctx.close()
+
+
+@pytest.mark.parametrize("rank", [1, 5, 7])
+def test_rank_specific_seed_windows_are_bit_exact(oracle, rank):
+    """SURVEY.md 4 "per-rank parity on a rank-specific slice": bench.py gives every rank its own window of the seed
+    space (shard.stream_seed_index). The streams ranks > 0 decode in the scaling runs are checked against the oracle
+    here on one GPU: all 64 distinct streams of that rank's window, last two pictures each."""
+    import bench
+    gen, streams = bench.make_streams(bench.DISTINCT, rank)
+    gen0, _ = bench.make_streams(2, 0)
+    assert not np.array_equal(gen[0][0][:4096], gen0[0][0][:4096])      # a different window from rank 0's
+    ctx = espflix_b200.Context(n_streams=len(streams), max_pictures=bench.PICTURES, es_capacity=sum(len(s) for s in streams) + 4096, fields=False)
+    blob, off = ctx.pack(streams)
+    ctx.submit_es(blob, off)
+    ctx.index()
+    ctx.decode_all(bench.PICTURES)
+    got = ctx.read_latest_i420()
+    for i in range(len(streams)):
+        want = oracle.decode_es(gen[i][0])
+        assert np.array_equal(got[i], want[-1]), "rank %d stream %d: %s" % (rank, i, _first_diff(got[i], want[-1]))
+        base = ctx.stream_info(i)[1]
+        prev = ctx.read_frame_i420(i, ((base + bench.PICTURES) & 1) ^ 1)
+        assert np.array_equal(prev, want[-2]), "rank %d stream %d previous picture" % (rank, i)
+    ctx.close()
