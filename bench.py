@@ -290,8 +290,11 @@ def run_gpu(args):
         streams = args.streams
     gen, stream_list = make_streams(streams, rank)
     sizes = np.diff(gen[0][1].astype(np.int64))
+    from espflix_b200 import synth
+    ts_distinct = [synth.wrap_ts(*g) for g in gen]            # the reference's wire format (188-byte TS, PID 0x100) of the same streams
+    ts_bytes_total = sum(len(ts_distinct[i % len(gen)]) for i in range(streams))
     ctx = espflix_b200.Context(n_streams=streams, max_pictures=PICTURES, max_slices_per_picture=12,
-                               es_capacity=sum(len(s) for s in stream_list) + 4096, device=local, fields=True)
+                               es_capacity=max(sum(len(s) for s in stream_list), ts_bytes_total) + 4096, device=local, fields=True)
     blob_np, off_np = ctx.pack(stream_list)
     es_bytes = int(off_np[-1])
     pinned_es = torch.empty(es_bytes, dtype=torch.uint8, pin_memory=True)
@@ -420,6 +423,32 @@ def run_gpu(args):
     e2e_ms = timed_host_loop(step_e2e, args.steps)
     clocks = sampler.summary() if rank == 0 else None
 
+    # e2e_ts: the same end-to-end step fed with transport streams (device-side TS/PES demux in front of the index)
+    e2e_ts_ms, ts_steps = None, 0
+    if not args.no_e2e_ts:
+        ts_off = np.zeros(streams + 1, dtype=np.uint64)
+        ts_off[1:] = np.cumsum([len(ts_distinct[i % len(gen)]) for i in range(streams)])
+        pinned_ts = torch.empty(int(ts_off[-1]), dtype=torch.uint8, pin_memory=True)
+        view = pinned_ts.numpy()
+        for i in range(streams):
+            view[int(ts_off[i]):int(ts_off[i + 1])] = ts_distinct[i % len(gen)]
+
+        def step_ts(k):
+            ctx.submit_ts(pinned_ts.data_ptr(), ts_off, st, device=False)
+            ctx.index(st)
+            ctx.decode_all(PICTURES, st)
+            ctx.read_latest_i420_async(0, streams, pinned_out[k & 1].data_ptr(), st)
+
+        ts_steps = max(1, min(args.steps, 10))
+        e2e_ts_ms = timed_host_loop(step_ts, ts_steps)
+        ts_total_bytes = int(ts_off[-1])
+        if not args.no_verify:
+            ctx.sync(st)
+            want = oracle.decode_es(gen[0][0])
+            if not np.array_equal(ctx.read_frame_i420(0, -1), want[-1]):
+                raise SystemExit("bench.py --verify: rank %d: TS-fed decode differs from the oracle" % rank)
+        del pinned_ts
+
     # e2e_all: every decoded picture handed to the host (12x the read-back of `e2e`): PCIe bound
     all_steps, e2e_all_ms, all_bytes = 0, None, PICTURES * streams * FRAME_BYTES
     if not args.no_e2e_all and all_bytes <= (8 << 30):
@@ -462,10 +491,11 @@ def run_gpu(args):
     frames_done = streams * PICTURES * args.steps
     link_min, link_sum = dict(link), dict(link)
     if dist is not None:
-        t = torch.tensor([ms_total, k1_ms, e2e_ms, e2e_all_ms or 0.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_total, k1_ms, e2e_ms, e2e_all_ms or 0.0, e2e_ts_ms or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, k1_ms, e2e_ms, e2e_all_max = [float(x) for x in t.tolist()]
+        ms_total, k1_ms, e2e_ms, e2e_all_max, e2e_ts_max = [float(x) for x in t.tolist()]
         e2e_all_ms = e2e_all_max if e2e_all_ms is not None else None
+        e2e_ts_ms = e2e_ts_max if e2e_ts_ms is not None else None
         lt = torch.tensor([link["h2d_gbs"], link["d2h_gbs"], link["both_gbs"]], device="cuda", dtype=torch.float64)
         lmin, lsum = lt.clone(), lt.clone()
         dist.all_reduce(lmin, op=dist.ReduceOp.MIN)
@@ -521,6 +551,10 @@ def run_gpu(args):
             line["e2e_all"] = {"value": (total_frames / args.steps * all_steps) / (e2e_all_ms / 1000.0), "unit": UNIT, "steps": all_steps,
                                "h2d_bytes_per_step": es_bytes + int(off_np.nbytes), "d2h_bytes_per_step": all_bytes, "ms_per_step": e2e_all_ms / all_steps,
                                "what": "per step: pinned ES -> ef_submit_es_host -> ef_index -> ef_decode_all_to_host(12): every decoded picture of every stream is exported after its reconstruction launch and copied to pinned host memory while the next picture index is rebuilt (the reference's push_video hand-over of every picture)"}
+        if e2e_ts_ms is not None:
+            line["e2e_ts"] = {"value": (total_frames / args.steps * ts_steps) / (e2e_ts_ms / 1000.0), "unit": UNIT, "steps": ts_steps,
+                              "h2d_bytes_per_step": ts_total_bytes, "d2h_bytes_per_step": streams * FRAME_BYTES, "ms_per_step": e2e_ts_ms / ts_steps,
+                              "what": "as e2e, but the input is the reference's wire format: 188-byte transport packets, PID 0x100, one PES per picture (ef_submit_ts_host: packet kernel + per-stream scan + compaction on the device, player.cpp:381-493)"}
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, orig_affinity)                       # the CPU arm uses every core the job may use, not the GPU's NUMA node only
             cores = best_process_count(gen)
@@ -547,6 +581,7 @@ def main():
     ap.add_argument("--total-streams", type=int, default=32768, help="strong scaling: streams of the whole job")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of this rank's first distinct streams after the timed region")
     ap.add_argument("--no-e2e-all", action="store_true", help="skip the all-pictures read-back leg (5 GB pinned per GPU)")
+    ap.add_argument("--no-e2e-ts", action="store_true", help="skip the transport-stream input leg")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -49,7 +49,7 @@ _SIGNATURES = {
     "ef_stream_info": (_I, [_VP, _I, ctypes.POINTER(_I), ctypes.POINTER(_I)]),
     "ef_decode_picture": (_I, [_VP, _I, _VP]),
     "ef_decode_all": (_I, [_VP, _I, _VP]),
-    "ef_decode_all_to_host": (_I, [_VP, _I, _VP, _VP]),
+    "ef_decode_all_to_host": (_I, [_VP, _I, _VP, _I, _VP]),
     "ef_read_frame": (_I, [_VP, _I, _I, _VP]),
     "ef_read_frame_i420": (_I, [_VP, _I, _I, _VP]),
     "ef_write_frame_i420": (_I, [_VP, _I, _I, _VP]),
@@ -67,9 +67,14 @@ _SIGNATURES = {
     "ef_video_isr": (_I, [_VP, _I, _I, _VP]),
     "ef_blit": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I]),
     "ef_launch_count": (ctypes.c_uint64, [_VP]),
+    "ef_host_alloc": (_I, [ctypes.POINTER(_VP), ctypes.c_size_t]),
+    "ef_host_free": (None, [_VP]),
     "ef_set_profiling": (_I, [_VP, _I]),
     "ef_stage_ms": (_I, [_VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "ef_tsidx_scan": (_I, [_I, _VP, _VP, _I, ctypes.c_uint32, _VP, _VP, _VP]),
+    "ef_idct_tc_run": (_I, [_I, _VP, _I, _VP, _VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _I]),
+    "ef_audio_demux_ts": (_I, [_I, _VP, _VP, _I, _VP, ctypes.c_uint64, _VP]),
+    "ef_audio_decode": (_I, [_I, _VP, _VP, _I, _VP, _VP, ctypes.c_uint64, _VP]),
     "ef_tsidx_samples": (_I, [_I, _VP, _VP, _I, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, _VP, ctypes.c_uint32, _VP]),
 }
 
@@ -166,9 +171,9 @@ class Context:
     def decode_all(self, n_pictures, stream=0):
         self._check(self.lib.ef_decode_all(self._h, n_pictures, stream))
 
-    def decode_all_to_host(self, n_pictures, out, stream=0):
-        """every picture of the submit to out[n_pictures][n_streams][I420] (pinned host memory; complete after sync())"""
-        self._check(self.lib.ef_decode_all_to_host(self._h, n_pictures, _ptr(out), stream))
+    def decode_all_to_host(self, n_pictures, out, stream=0, strips=False):
+        """every picture of the submit to out[n_pictures][n_streams][I420 or strips] (pinned host memory; complete after sync())"""
+        self._check(self.lib.ef_decode_all_to_host(self._h, n_pictures, _ptr(out), 1 if strips else 0, stream))
 
     def read_frame(self, s, fb=-1):
         out = np.empty(FRAME_BYTES, dtype=np.uint8)
@@ -313,6 +318,50 @@ def tsidx_samples(seq_pts, seq_pos, first_pts, last_pts, bin_size=IDX_BIN, devic
     _check_rc(lib, lib.ef_tsidx_samples(device, seq_pts.ctypes.data, seq_pos.ctypes.data, len(seq_pts), first_pts, last_pts, bin_size,
                                         out.ctypes.data, cap, ctypes.byref(n)))
     return out[:n.value].copy()
+
+
+def idct_tc_run(coefs, L, repeats=5, device=0):
+    """The tcgen05 IDCT experiment (include/espflix_b200.h): coefs int32 [n][64], L float64 [64][64] -> (out int32 [n][64], prep_ms, mma_ms)"""
+    lib = load_library()
+    coefs = np.ascontiguousarray(coefs, dtype=np.int32)
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    out = np.zeros_like(coefs)
+    a, b = ctypes.c_float(), ctypes.c_float()
+    _check_rc(lib, lib.ef_idct_tc_run(device, coefs.ctypes.data, coefs.shape[0], L.ctypes.data, out.ctypes.data, ctypes.byref(a), ctypes.byref(b), repeats))
+    return out, a.value, b.value
+
+
+# -- audio (src/sbc_decoder.cpp, espflix.ino pdm_second_order; SURVEY.md 8f-3) ------------------------------------------
+_AUDIO_INFO = np.dtype([("frame_size", "<i4"), ("n_frames", "<u4"), ("pcm_offset", "<u8")])
+
+
+def audio_demux_ts(files, device=0):
+    """The bytes push_audio() receives (PID 0x101 / 0x102) for a list of transport streams -> list of uint8 arrays."""
+    lib = load_library()
+    blob, off = Context.pack(files)
+    es = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+    es_off = np.zeros(len(files) + 1, dtype=np.uint64)
+    _check_rc(lib, lib.ef_audio_demux_ts(device, blob.ctypes.data, off.ctypes.data, len(files), es.ctypes.data, es.size, es_off.ctypes.data))
+    return [es[int(es_off[i]):int(es_off[i + 1])].copy() for i in range(len(files))]
+
+
+def audio_decode(streams, pdm=True, device=0):
+    """decode_audio() for a list of SBC byte streams -> list of dicts: frame_size, n_frames, pcm (int16), pdm (uint16 or None)."""
+    lib = load_library()
+    blob, off = Context.pack(streams)
+    info = np.zeros(len(streams), dtype=_AUDIO_INFO)
+    _check_rc(lib, lib.ef_audio_decode(device, blob.ctypes.data, off.ctypes.data, len(streams), info.ctypes.data, None, 0, None))
+    n = int(sum(int(i["n_frames"]) for i in info)) * 128
+    pcm = np.zeros(max(n, 1), dtype=np.int16)
+    pd = np.zeros(max(2 * n, 1), dtype=np.uint16) if pdm else None
+    _check_rc(lib, lib.ef_audio_decode(device, blob.ctypes.data, off.ctypes.data, len(streams), info.ctypes.data, pcm.ctypes.data, pcm.size,
+                                       None if pd is None else pd.ctypes.data))
+    out = []
+    for i in info:
+        a, k = int(i["pcm_offset"]), int(i["n_frames"]) * 128
+        out.append({"frame_size": int(i["frame_size"]), "n_frames": int(i["n_frames"]), "pcm": pcm[a:a + k].copy(),
+                    "pdm": None if pd is None else pd[2 * a:2 * (a + k)].copy()})
+    return out
 
 
 def build_video_idx(video_ts, fwd_ts, rev_ts, device=0):

@@ -21,16 +21,25 @@ __global__ void ef_scan_kernel(EfDev* Dp);
 __global__ void ef_prefix_kernel(EfDev* Dp);
 __global__ void ef_fill_kernel(EfDev* Dp);
 __global__ void ef_ts_len_kernel(const uint8_t* ts, uint64_t n_packets, uint32_t* out_len);
-__global__ void ef_ts_copy_kernel(const uint8_t* ts, uint64_t n_packets, const uint64_t* out_off, uint8_t* es);
-__global__ void ef_ts_scan_kernel(const uint32_t* len, uint64_t n_packets, uint64_t* off, const uint64_t* ts_off, int n_streams, uint64_t* es_off, uint8_t* es);
+__global__ void ef_ts_copy_kernel(const uint8_t* ts, uint64_t n_packets, const uint32_t* local_off, const uint16_t* pkt_stream, const uint64_t* es_off, uint8_t* es);
+__global__ void ef_ts_scan_kernel(const uint32_t* len, const uint64_t* ts_off, uint32_t* local_off, uint16_t* pkt_stream, uint64_t* stream_total);
+__global__ void ef_ts_offsets_kernel(const uint64_t* stream_total, int n_streams, uint64_t* es_off, uint8_t* es);
 size_t ef_recon_smem_bytes();
 cudaError_t ef_decode_configure();
 int ef_decode_resident_ctas(int which);
 __global__ void ef_tsidx_packet_kernel(const uint8_t* ts, const uint64_t* pkt_off, int n_files, uint64_t n_packets, int64_t* pkt_pts, uint8_t* pkt_kind);
 __global__ void ef_tsidx_compact_kernel(const uint64_t* pkt_off, const int64_t* pkt_pts, const uint8_t* pkt_kind, int64_t* seq_pts, uint32_t* seq_pos, int64_t* info);
 __global__ void ef_tsidx_sample_kernel(const int64_t* seq_pts, const uint32_t* seq_pos, int n, int64_t first_pts, uint32_t bin_size, uint32_t n_samples, uint32_t* samples);
-cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream);
-cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, cudaStream_t stream);
+__global__ void ef_sbc_probe_kernel(const uint8_t* es, const uint64_t* off, int n_streams, int* frame_size);
+__global__ void ef_sbc_matrix_kernel(const uint8_t* es, const uint64_t* off, const int* frame_size, const uint64_t* slot_base, int n_streams, int32_t* vrows);
+__global__ void ef_sbc_window_kernel(const int32_t* vrows, const uint64_t* slot_base, const uint64_t* pcm_off, int n_streams, int16_t* pcm);
+__global__ void ef_pdm_kernel(const int16_t* pcm, const uint64_t* pcm_off, int n_streams, uint16_t* pdm);
+__global__ void ef_audio_ts_packet_kernel(const uint8_t* ts, uint64_t n_packets, uint8_t* start, uint8_t* kind);
+__global__ void ef_audio_ts_scan_kernel(const uint64_t* pkt_off, int n_files, const uint8_t* start, const uint8_t* kind, uint32_t* out_pos, uint64_t* es_len);
+__global__ void ef_audio_ts_copy_kernel(const uint8_t* ts, const uint64_t* pkt_off, int n_files, uint64_t n_packets, const uint8_t* start, const uint32_t* out_pos, const uint64_t* es_off, uint8_t* es);
+cudaError_t ef_audio_upload_constants();
+cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, size_t max_slices, cudaStream_t stream);
+cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, size_t n_slots, cudaStream_t stream);
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream);
 cudaError_t ef_launch_blit(const EfDev* dev, int stream_index, int fb, int line, int x, int width, int frame_counter, uint16_t* dst, cudaStream_t stream);
 
@@ -130,7 +139,9 @@ struct ef_ctx {
     int stage_idx = 0;
     uint8_t* d_ts = nullptr;  // TS staging (same capacity) + packet tables, allocated on first TS submit
     uint32_t* d_pkt_len = nullptr;
-    uint64_t* d_pkt_off = nullptr;
+    uint32_t* d_pkt_off = nullptr;   // payload offset of a packet inside its stream's ES
+    uint16_t* d_pkt_stream = nullptr;
+    uint64_t* d_stream_total = nullptr;
     uint64_t* d_ts_off = nullptr;
     uint8_t* d_stage = nullptr;      // read-back staging (I420 / strips)
     size_t stage_bytes = 0;
@@ -368,6 +379,8 @@ static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, boo
             if ((rc = dev_alloc(c, &c->d_ts, c->cfg.es_capacity + 64)) != EF_OK) return rc;
             if ((rc = dev_alloc(c, &c->d_pkt_len, c->cfg.es_capacity / 188 + 1)) != EF_OK) return rc;
             if ((rc = dev_alloc(c, &c->d_pkt_off, c->cfg.es_capacity / 188 + 1)) != EF_OK) return rc;
+            if ((rc = dev_alloc(c, &c->d_pkt_stream, c->cfg.es_capacity / 188 + 1)) != EF_OK) return rc;
+            if ((rc = dev_alloc(c, &c->d_stream_total, (size_t)n + 1)) != EF_OK) return rc;
             if ((rc = dev_alloc(c, &c->d_ts_off, (size_t)n + 1)) != EF_OK) return rc;
         }
         CK(cudaMemcpyAsync(c->d_ts, src, total, kind, up));
@@ -375,11 +388,13 @@ static int submit_common(ef_ctx* c, const uint8_t* src, const uint64_t* off, boo
         if (n_packets) {
             ef_ts_len_kernel<<<(unsigned)((n_packets + 255) / 256), 256, 0, up>>>(c->d_ts, n_packets, c->d_pkt_len);
             CK(cudaGetLastError());
-            ef_ts_scan_kernel<<<1, 1024, 0, up>>>(c->d_pkt_len, n_packets, c->d_pkt_off, c->d_ts_off, n, d_es_off, d_es);
+            ef_ts_scan_kernel<<<n, 256, 0, up>>>(c->d_pkt_len, c->d_ts_off, c->d_pkt_off, c->d_pkt_stream, c->d_stream_total);
             CK(cudaGetLastError());
-            ef_ts_copy_kernel<<<(unsigned)((n_packets * 32 + 255) / 256), 256, 0, up>>>(c->d_ts, n_packets, c->d_pkt_off, d_es);
+            ef_ts_offsets_kernel<<<1, 1024, 0, up>>>(c->d_stream_total, n, d_es_off, d_es);
             CK(cudaGetLastError());
-            c->launches += 3;
+            ef_ts_copy_kernel<<<(unsigned)((n_packets * 32 + 255) / 256), 256, 0, up>>>(c->d_ts, n_packets, c->d_pkt_off, c->d_pkt_stream, d_es_off, d_es);
+            CK(cudaGetLastError());
+            c->launches += 4;
         } else CK(cudaMemsetAsync(d_es_off, 0, ((size_t)n + 1) * 8, up));
     }
     CK(cudaEventRecord(c->ev_up_done[b], up));
@@ -410,7 +425,7 @@ int ef_index(ef_ctx* c, void* stream)
     CK(cudaMemsetAsync(c->h.info, 0, 32, st));
     ef_scan_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(c->d);
     CK(cudaGetLastError());
-    ef_prefix_kernel<<<1, 1024, 0, st>>>(c->d);
+    ef_prefix_kernel<<<c->h.max_pictures, 1024, 0, st>>>(c->d);
     CK(cudaGetLastError());
     const size_t threads = (size_t)n * c->h.max_pictures;
     ef_fill_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->d);
@@ -470,25 +485,25 @@ static int ensure_stage2(ef_ctx* c, int k, size_t bytes)
 // K1a over picture indices [p0, p0 + k), then K1b once per picture index. host_dst != nullptr: every picture index
 // is exported (I420) straight after its K1b launch and copied to host_dst[p][stream] on the read-back stream while
 // the next picture index is being rebuilt - what push_video() sees, picture by picture (video.h:49).
-static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st, uint8_t* host_dst = nullptr)
+static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st, uint8_t* host_dst = nullptr, int layout = 0)
 {
     DeviceScope scope_(c ? c->cfg.device : -1);
     const size_t slots = (size_t)k * c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX;
     CK(cudaMemsetAsync(c->h.mb_info, 0, slots * 4, st));
     CK(cudaMemsetAsync(c->h.parse_cursor, 0, ((size_t)k + 1) * 4, st));
     if (c->profiling) { CK(cudaEventRecord(c->ev_prof[2], st)); c->prof_decode = true; }
-    CK(ef_launch_parse(c->d, p0, k, c->sm_count, st));
+    CK(ef_launch_parse(c->d, p0, k, c->sm_count, (size_t)k * c->cfg.n_streams * c->cfg.max_slices_per_picture, st));
     if (c->profiling) CK(cudaEventRecord(c->ev_prof[3], st));
     const size_t batch_bytes = (size_t)c->cfg.n_streams * EF_FRAME;
     for (int i = 0; i < k; i++) {
-        CK(ef_launch_recon(c->d, i, c->sm_count, st));
+        CK(ef_launch_recon(c->d, i, c->sm_count, (size_t)c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX, st));
         if (host_dst) {
             const int b = c->stage_idx ^= 1;
             int rc = ensure_stage2(c, b, batch_bytes);
             if (rc != EF_OK) return rc;
             CK(cudaStreamWaitEvent(st, c->ev_down_done[b], 0));            // the previous copy out of this staging buffer has finished
             const uint64_t threads = (uint64_t)c->cfg.n_streams * (EF_FRAME / 8);
-            ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, 0, c->cfg.n_streams, -2 - (p0 + i), 0, c->d_stage2[b]);
+            ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, 0, c->cfg.n_streams, -2 - (p0 + i), layout, c->d_stage2[b]);
             CK(cudaGetLastError());
             c->launches++;
             CK(cudaEventRecord(c->ev_export, st));
@@ -524,14 +539,15 @@ int ef_decode_all(ef_ctx* c, int n_pictures, void* stream)
     return EF_OK;
 }
 
-int ef_decode_all_to_host(ef_ctx* c, int n_pictures, uint8_t* dst, void* stream)
+int ef_decode_all_to_host(ef_ctx* c, int n_pictures, uint8_t* dst, int layout, void* stream)
 {
     if (!c || !dst) return fail(EF_EINVAL, "null argument");
+    if (layout != 0 && layout != 1) return fail(EF_EINVAL, "layout must be 0 (I420) or 1 (strips)");
     if (!c->indexed) return fail(EF_ESTATE, "ef_decode_all_to_host before ef_index");
     if (n_pictures < 0 || n_pictures > c->cfg.max_pictures) return fail(EF_EINVAL, "n_pictures %d out of range", n_pictures);
     for (int p = 0; p < n_pictures; p += c->h.rec_pics) {
         const int k = n_pictures - p < c->h.rec_pics ? n_pictures - p : c->h.rec_pics;
-        int rc = decode_range(c, p, k, (cudaStream_t)stream, dst);
+        int rc = decode_range(c, p, k, (cudaStream_t)stream, dst, layout);
         if (rc != EF_OK) return rc;
     }
     return EF_OK;
@@ -756,6 +772,15 @@ int ef_blit(ef_ctx* c, int stream_index, int fb, uint16_t* dst, int line, int x,
 
 uint64_t ef_launch_count(ef_ctx* c) { return c ? c->launches : 0; }
 
+int ef_host_alloc(void** p, size_t bytes)
+{
+    if (!p || !bytes) return fail(EF_EINVAL, "null argument");
+    CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return EF_OK;
+}
+
+void ef_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int ef_set_profiling(ef_ctx* c, int on)
 {
     DeviceScope scope_(c ? c->cfg.device : -1);
@@ -854,6 +879,103 @@ int ef_tsidx_samples(int device, const int64_t* seq_pts, const uint32_t* seq_pos
     ef_tsidx_sample_kernel<<<(n + 127) / 128, 128>>>((const int64_t*)d_pts.p, (const uint32_t*)d_pos.p, n_seq, first_pts, bin_size, n, (uint32_t*)d_out.p);
     CK(cudaGetLastError());
     CK(cudaMemcpy(samples, d_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return EF_OK;
+}
+
+// ---- audio: SBC decode + PDM, stateless --------------------------------------------------------
+static int audio_device(int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || ndev <= device) return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", device, cudaGetErrorString(e));
+    return EF_OK;
+}
+
+int ef_audio_demux_ts(int device, const uint8_t* ts, const uint64_t* off, int n_files, uint8_t* es, uint64_t es_cap, uint64_t* es_off)
+{
+    if (!ts || !off || !es_off || n_files < 1) return fail(EF_EINVAL, "null argument");
+    int rc = audio_device(device);
+    if (rc != EF_OK) return rc;
+    DeviceScope scope_(device);
+    for (int f = 0; f <= n_files; f++) if (off[f] % 188 || (f && off[f] < off[f - 1])) return fail(EF_EINVAL, "offsets must be non-decreasing multiples of 188");
+    const uint64_t total = off[n_files] - off[0], n_packets = total / 188;
+    std::vector<uint64_t> poff((size_t)n_files + 1);
+    for (int f = 0; f <= n_files; f++) poff[f] = (off[f] - off[0]) / 188;
+    DevBuf d_ts, d_start, d_kind, d_off, d_pos, d_len, d_esoff, d_es;
+    CK(d_ts.alloc(total)); CK(d_start.alloc(n_packets)); CK(d_kind.alloc(n_packets)); CK(d_off.alloc(poff.size() * 8));
+    CK(d_pos.alloc(n_packets * 4)); CK(d_len.alloc((size_t)n_files * 8)); CK(d_esoff.alloc(poff.size() * 8));
+    CK(cudaMemcpy(d_ts.p, ts + off[0], total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off.p, poff.data(), poff.size() * 8, cudaMemcpyHostToDevice));
+    if (n_packets) {
+        ef_audio_ts_packet_kernel<<<(unsigned)((n_packets + 255) / 256), 256>>>((const uint8_t*)d_ts.p, n_packets, (uint8_t*)d_start.p, (uint8_t*)d_kind.p);
+        CK(cudaGetLastError());
+    }
+    ef_audio_ts_scan_kernel<<<(n_files + 63) / 64, 64>>>((const uint64_t*)d_off.p, n_files, (const uint8_t*)d_start.p, (const uint8_t*)d_kind.p, (uint32_t*)d_pos.p, (uint64_t*)d_len.p);
+    CK(cudaGetLastError());
+    std::vector<uint64_t> len((size_t)n_files);
+    CK(cudaMemcpy(len.data(), d_len.p, len.size() * 8, cudaMemcpyDeviceToHost));
+    es_off[0] = 0;
+    for (int f = 0; f < n_files; f++) es_off[f + 1] = es_off[f] + len[f];
+    if (es_off[n_files] > es_cap || (!es && es_off[n_files])) return fail(EF_ENOMEM, "%llu audio bytes, capacity %llu", (unsigned long long)es_off[n_files], (unsigned long long)es_cap);
+    if (es_off[n_files]) {
+        CK(d_es.alloc(es_off[n_files]));
+        CK(cudaMemcpy(d_esoff.p, es_off, poff.size() * 8, cudaMemcpyHostToDevice));
+        ef_audio_ts_copy_kernel<<<(unsigned)((n_packets * 32 + 255) / 256), 256>>>((const uint8_t*)d_ts.p, (const uint64_t*)d_off.p, n_files, n_packets,
+                                                                                   (const uint8_t*)d_start.p, (const uint32_t*)d_pos.p, (const uint64_t*)d_esoff.p, (uint8_t*)d_es.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(es, d_es.p, es_off[n_files], cudaMemcpyDeviceToHost));
+    }
+    return EF_OK;
+}
+
+int ef_audio_decode(int device, const uint8_t* sbc, const uint64_t* off, int n_streams, ef_audio_info* info, int16_t* pcm, uint64_t pcm_cap, uint16_t* pdm)
+{
+    if (!sbc || !off || !info || n_streams < 1) return fail(EF_EINVAL, "null argument");
+    int rc = audio_device(device);
+    if (rc != EF_OK) return rc;
+    DeviceScope scope_(device);
+    for (int s = 0; s < n_streams; s++) if (off[s] > off[s + 1]) return fail(EF_EINVAL, "stream offsets must be non-decreasing");
+    static bool constants = false;                       // per process; every device gets its copy on first use
+    static int constants_dev = -1;
+    if (!constants || constants_dev != device) { CK(ef_audio_upload_constants()); constants = true; constants_dev = device; }
+    const uint64_t total = off[n_streams] - off[0];
+    std::vector<uint64_t> roff((size_t)n_streams + 1);
+    for (int s = 0; s <= n_streams; s++) roff[s] = off[s] - off[0];
+    DevBuf d_es, d_off, d_fs, d_slot, d_poff, d_v, d_pcm, d_pdm;
+    CK(d_es.alloc(total + 16)); CK(d_off.alloc(roff.size() * 8)); CK(d_fs.alloc((size_t)n_streams * 4));
+    CK(cudaMemcpy(d_es.p, sbc + off[0], total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off.p, roff.data(), roff.size() * 8, cudaMemcpyHostToDevice));
+    ef_sbc_probe_kernel<<<(n_streams + 127) / 128, 128>>>((const uint8_t*)d_es.p, (const uint64_t*)d_off.p, n_streams, (int*)d_fs.p);
+    CK(cudaGetLastError());
+    std::vector<int> fs((size_t)n_streams);
+    CK(cudaMemcpy(fs.data(), d_fs.p, fs.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> slot((size_t)n_streams + 1, 0), poff((size_t)n_streams + 1, 0);
+    for (int s = 0; s < n_streams; s++) {
+        const uint64_t len = roff[s + 1] - roff[s];
+        const uint32_t frames = fs[s] > 0 ? (uint32_t)(len / (uint64_t)fs[s]) : 0u;
+        info[s].frame_size = fs[s]; info[s].n_frames = frames; info[s].pcm_offset = poff[s];
+        slot[s + 1] = slot[s] + (fs[s] > 0 ? (uint64_t)frames + 1 : 0);      // + the probe decode of frame 0
+        poff[s + 1] = poff[s] + (uint64_t)frames * 128;
+    }
+    const uint64_t n_pcm = poff[n_streams];
+    if (!pcm) return EF_OK;                                  // sizing call
+    if (n_pcm > pcm_cap) return fail(EF_ENOMEM, "%llu PCM samples, capacity %llu", (unsigned long long)n_pcm, (unsigned long long)pcm_cap);
+    if (!n_pcm) return EF_OK;
+    CK(d_slot.alloc(slot.size() * 8)); CK(d_poff.alloc(poff.size() * 8));
+    CK(d_v.alloc(slot[n_streams] * 16 * 16 * 4)); CK(d_pcm.alloc(n_pcm * 2));
+    CK(cudaMemcpy(d_slot.p, slot.data(), slot.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_poff.p, poff.data(), poff.size() * 8, cudaMemcpyHostToDevice));
+    ef_sbc_matrix_kernel<<<(unsigned)((slot[n_streams] + 3) / 4), 128>>>((const uint8_t*)d_es.p, (const uint64_t*)d_off.p, (const int*)d_fs.p, (const uint64_t*)d_slot.p, n_streams, (int32_t*)d_v.p);
+    CK(cudaGetLastError());
+    ef_sbc_window_kernel<<<(unsigned)((n_pcm + 255) / 256), 256>>>((const int32_t*)d_v.p, (const uint64_t*)d_slot.p, (const uint64_t*)d_poff.p, n_streams, (int16_t*)d_pcm.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(pcm, d_pcm.p, n_pcm * 2, cudaMemcpyDeviceToHost));
+    if (pdm) {
+        CK(d_pdm.alloc(n_pcm * 4));
+        ef_pdm_kernel<<<(n_streams + 31) / 32, 32>>>((const int16_t*)d_pcm.p, (const uint64_t*)d_poff.p, n_streams, (uint16_t*)d_pdm.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(pdm, d_pdm.p, n_pcm * 4, cudaMemcpyDeviceToHost));
+    }
     return EF_OK;
 }
 

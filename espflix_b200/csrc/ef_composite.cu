@@ -19,6 +19,31 @@ __device__ __forceinline__ uint32_t chroma_word(const uint32_t* tab, uint32_t u,
     return ((tab[u & 255] + tab[vt + (v & 255)]) & 0xFCFCFCFCu) >> 2;      // CHROMA_EVEN / CHROMA_ODD, video.cpp:670
 }
 
+// The chroma LUTs have a closed form (tests/test_tables.py::test_chroma_lut_closed_form checks all 768 entries of
+// both standards): the four subcarrier phases of a table entry are 48, 48 +- r(c) with
+//   r(c) = sgn(128 - c) * ((16 |128 - c| + 11) / 22)          [= round_half_away((128 - c) * 24 / 33), espflix.cpp:1091-1180]
+// clamped to [0, 127]: U rides on the sine phases (bytes 1, 0), V on the cosine phases (bytes 3, 2; swapped on the PAL
+// lines that use cos_v_neg). EF_K2_ARITH computes CHROMA_EVEN / CHROMA_ODD from that instead of two dependent gathers.
+#ifndef EF_K2_ARITH
+#define EF_K2_ARITH 0
+#endif
+__device__ __forceinline__ int chroma_r(uint32_t c)
+{
+    const int d = 128 - (int)(c & 255u);
+    const int q = ((16 * abs(d) + 11) * 745) >> 14;                       // / 22, exact for numerators <= 2059 (tests/test_tables.py)
+    return d < 0 ? -q : q;
+}
+__device__ __forceinline__ uint32_t chroma_word_arith(uint32_t u, uint32_t v, bool v_neg)
+{
+    const int ru = chroma_r(u);
+    int rv = chroma_r(v);
+    if (v_neg) rv = -rv;
+    const uint32_t b3 = (uint32_t)__viaddmin_s32_relu(48, rv, 127), b2 = (uint32_t)__viaddmin_s32_relu(48, -rv, 127);
+    const uint32_t b1 = (uint32_t)__viaddmin_s32_relu(48, ru, 127), b0 = (uint32_t)__viaddmin_s32_relu(48, -ru, 127);
+    const uint32_t w = (b3 << 24) + (b2 << 16) + (b1 << 8) + b0 + 0x30303030u;       // + the constant phase of the other table
+    return (w & 0xFCFCFCFCu) >> 2;
+}
+
 // compile-time geometry of the two standards (video_init / pal_init, video.cpp:572-630; values
 // probe-verified against the reference in tests/golden/composite_pins.json)
 template <bool kNtsc> struct Geo;
@@ -106,21 +131,42 @@ __device__ __forceinline__ uint4 blit_quad(uint32_t y4, uint32_t dither, uint32_
 }
 
 #ifndef EF_K2_LEGACY
-// ---- K2 v5: a CTA synthesises a BAND of 16 consecutive lines of one stream in shared memory and hands every
-// finished line to the TMA engine (cp.async.bulk.global.shared::cta): the field leaves the SM as 1,824-byte
-// (PAL 2,272-byte) bulk stores instead of 16-byte STG, which took the output off the L1/TEX pipe - the v4 kernel
-// was bound there (86 % busy at 42 % DRAM throughput, profiles/r01_k2_details.txt). Bands coincide with
-// macroblock rows of the tiled frame (the active area starts at line 32 / 64), so the loads can follow the
-// tile layout: a warp takes two 8-pixel groups x 16 rows = 256 contiguous luma bytes and 2 x 64 contiguous chroma
-// bytes of ONE tile (2 + 1 + 1 L1 wavefronts instead of 8 + 8 + 8 when its lanes ran along a scan line).
-// Shared-memory lines are padded by 16 bytes: the 16-byte stores of 8 consecutive rows then hit 32 distinct banks.
+// ---- K2 v6: a CTA synthesises a BAND of 16 consecutive lines of one stream in shared memory and hands the finished
+// rows to the TMA engine (cp.async.bulk.global.shared::cta): the field leaves the SM as bulk stores instead of 16-byte
+// STG, which took the output off the L1/TEX pipe - the v4 kernel was bound there (86 % busy at 42 % DRAM throughput,
+// profiles/r01_k2_details.txt). Bands coincide with macroblock rows of the tiled frame (the active area starts at
+// line 32 / 64), so the loads follow the tile layout: a warp takes two 8-pixel groups x 16 rows = 256 contiguous luma
+// bytes and 2 x 64 contiguous chroma bytes of ONE tile (2 + 1 + 1 L1 wavefronts instead of 8 + 8 + 8 when its lanes
+// ran along a scan line). What is NOT picture is constant and is not recomputed per line (v5 did, and was bound by
+// instruction issue: profiles/r02_k2v5_ncu.txt):
+//   * a blank band synthesises each DISTINCT line once (NTSC: one; PAL: two burst phases; the vertical sync types; the
+//     overlay lines) and bulk-stores that one shared-memory row to every field line that shows it;
+//   * an active band synthesises sync / burst / black margins for two rows (the two PAL burst phases) and stores every
+//     line as three bulk copies: left margin and right margin from the template row, the blit span from the line's own.
+// Shared-memory rows are padded by 16 bytes: the 16-byte stores of 8 consecutive rows then hit 32 distinct banks.
 // grid: x = band (17 NTSC / 20 PAL), y = stream; 352 threads = 11 warps x 2 tile columns = the 22 macroblocks of a row.
-constexpr int kK2Threads = 352;
+#ifndef EF_K2_THREADS
+#define EF_K2_THREADS 352
+#endif
+constexpr int kK2Threads = EF_K2_THREADS;             // 352 (2 tile-column tasks per warp) or 704 (1)
+constexpr int kK2Tasks = 22 / (kK2Threads / 32);
+static_assert(kK2Tasks * (kK2Threads / 32) == 22, "the 22 macroblock columns of a row must divide over the warps");
 
-__device__ __forceinline__ void bulk_store_line(void* gdst, const void* ssrc, uint32_t bytes)
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+// which blank lines look alike: lines of one class are sample-identical
+template <bool kNtsc>
+__device__ __forceinline__ int blank_class(const EfPresent& pr, int line)
+{
+    using G = Geo<kNtsc>;
+    if (line >= G::VSYNC) return kNtsc ? 1 : 16 + (int)((0x00233000u >> ((line - G::VSYNC) * 4)) & 15u);   // _sync_type[], as in blank_sample()
+    const int ol = line - (G::TOP + EF_H + 2);
+    if (pr.blend != 0 && ol >= 0 && ol < 16) return 64 + ol;              // overlay rows differ line by line
+    return kNtsc ? 0 : ((line + 1) & 1) + 2;                              // PAL: the burst table alternates (burst_pal())
 }
 
 template <bool kNtsc>
@@ -131,7 +177,9 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter,
     constexpr int CPL = G::W / 8;                                          // 16-byte chunks per line
     constexpr int LB = G::W * 2, LS = LB + 16;                             // bytes per line in the field / in shared memory
     constexpr int BLIT_C = G::BLIT / 8, BLIT_N = 2 * EF_W / 8;             // the blit span in chunks: [BLIT_C, BLIT_C + 88)
+    constexpr int MARGIN_N = CPL - BLIT_N;                                 // chunks of a line outside it
     __shared__ __align__(128) uint8_t sm[16 * LS];
+    __shared__ int s_src[16], s_distinct[16], s_n;
     const EfDev& D = *Dp;
     const uint32_t* tab = D.color_tab;                                     // 3 KB chroma LUT through L1
     const int stream = (int)blockIdx.y;
@@ -139,16 +187,44 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter,
     const int nlines = min(16, G::LINES - line0);
     const int fl0 = line0 - G::TOP;                                        // frame line of the band's first line (bands = macroblock rows)
     const bool active = fl0 >= 0 && fl0 < EF_H && fb_sel != -2;            // -2: no frame presented yet (video.cpp:1140)
+    uint16_t* out0 = D.fields + (size_t)stream * D.field_stride + (size_t)line0 * G::W;
 
-    // sync, burst, black level, vertical sync, overlay: every chunk outside the blit span
-    const int per_line = active ? CPL - BLIT_N : CPL;
-    for (int i = (int)threadIdx.x; i < per_line * nlines; i += kK2Threads) {
-        const int l = i / per_line, k = i - l * per_line;
-        const int c = (active && k >= BLIT_C) ? k + BLIT_N : k;
-        *(uint4*)(sm + l * LS + c * 16) = blank_chunk<kNtsc>(D, pr, line0 + l, c * 8);
+    if (!active) {
+        // ---- blank band: every distinct line once ------------------------------------------------------------------
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int l = 0; l < nlines; l++) {
+                const int c = blank_class<kNtsc>(pr, line0 + l);
+                int src = l;
+                for (int k = 0; k < l; k++) if (blank_class<kNtsc>(pr, line0 + k) == c) { src = k; break; }
+                s_src[l] = src;
+                if (src == l) s_distinct[n++] = l;
+            }
+            s_n = n;
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (int i = (int)threadIdx.x; i < n * CPL; i += kK2Threads) {
+            const int l = s_distinct[i / CPL], c = i % CPL;
+            *(uint4*)(sm + l * LS + c * 16) = blank_chunk<kNtsc>(D, pr, line0 + l, c * 8);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy
+        __syncthreads();
+        if ((int)threadIdx.x < nlines) {
+            bulk_store(out0 + (size_t)threadIdx.x * G::W, sm + s_src[threadIdx.x] * LS, LB);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must stay valid until the engine has read it
+        }
+        return;
     }
 
-    if (active) {
+    // ---- active band: margins of the two template rows (rows 0 and 1: even / odd field line) ----------------------------
+    for (int i = (int)threadIdx.x; i < 2 * MARGIN_N; i += kK2Threads) {
+        const int l = i / MARGIN_N, k = i % MARGIN_N;
+        const int c = k >= BLIT_C ? k + BLIT_N : k;
+        *(uint4*)(sm + l * LS + c * 16) = blank_chunk<kNtsc>(D, pr, line0 + l, c * 8);
+    }
+    {
         const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
         const int row = lane & 15, fl = fl0 + row;                         // frame line 0..191
         int fb0 = fb_sel >= 0 ? fb_sel : (int)((D.base_pics[stream] + D.n_pics[stream]) & 1u);
@@ -160,42 +236,62 @@ ef_composite_kernel(const EfDev* __restrict__ Dp, int fb_sel, int frame_counter,
         const int cy = fl >> 1, ncy = cy + (fl == 191 ? 0 : 1);            // odd lines average with the next chroma row (video.cpp:704-716)
         const int yoff = (fl >> 4) * EF_MBW_MAX * EF_TILE + (fl & 15) * 16;
         const int coff = (cy >> 3) * EF_MBW_MAX * EF_TILE + (cy & 7) * 8 + 256;      // get_cr(line>>1); get_cb is the next 64-byte plane
-        const int noff = (ncy >> 3) * EF_MBW_MAX * EF_TILE + (ncy & 7) * 8 + 256;
+        const int noff = (fl & 1) ? (ncy >> 3) * EF_MBW_MAX * EF_TILE + (ncy & 7) * 8 + 256 : coff;
         const int vt = (fl & 1) ? 512 : 256;
-        for (int gd = warp * 2 + (lane >> 4); gd < 2 * EF_W / 16; gd += (kK2Threads / 32) * 2) {   // destination group 0..43
+        const uint8_t* fbase = D.frames + ef_frame_offset(stream, 0);
+        // the warp's two tasks (destination groups gd and gd + 22): all loads first, then the arithmetic
+        uint32_t u4[kK2Tasks], v4[kK2Tasks], un[kK2Tasks], vn[kK2Tasks], lumw[kK2Tasks];
+        uint2 y8[kK2Tasks];
+        bool cstart[kK2Tasks];
+#pragma unroll
+        for (int t = 0; t < kK2Tasks; t++) {
+            const int gd = warp * 2 + (lane >> 4) + t * (44 / kK2Tasks);   // destination group 0..43
             const bool second = gd >= split;
             const int g = second ? gd - split : gd + (h >> 3);             // 8-pixel group of the source frame
-            const bool call_start = second ? g == 0 : gd == 0;             // blit() starts its luma carry at 0
-            const uint8_t* f = D.frames + ef_frame_offset(stream, fb0 ^ (int)second);
+            cstart[t] = second ? g == 0 : gd == 0;                         // blit() starts its luma carry at 0
+            const uint8_t* f = fbase + (size_t)(fb0 ^ (int)second) * EF_FRAME;
             const int tcol = (g >> 1) * EF_TILE, sub = g & 1;
-            uint32_t u4 = *(const uint32_t*)(f + coff + tcol + sub * 4);
-            uint32_t v4 = *(const uint32_t*)(f + coff + tcol + sub * 4 + 64);
+            u4[t] = *(const uint32_t*)(f + coff + tcol + sub * 4);
+            v4[t] = *(const uint32_t*)(f + coff + tcol + sub * 4 + 64);
+            un[t] = *(const uint32_t*)(f + noff + tcol + sub * 4);
+            vn[t] = *(const uint32_t*)(f + noff + tcol + sub * 4 + 64);
+            y8[t] = *(const uint2*)(f + yoff + tcol + sub * 8);
+            const int q = cstart[t] ? 0 : 2 * g - 1;                       // previous 4-pixel group
+            lumw[t] = *(const uint32_t*)(f + yoff + (q >> 2) * EF_TILE + (q & 3) * 4);
+        }
+#pragma unroll
+        for (int t = 0; t < kK2Tasks; t++) {
+            const int gd = warp * 2 + (lane >> 4) + t * (44 / kK2Tasks);
+            uint32_t u = u4[t], v = v4[t];
             if (fl & 1) {
-                u4 = ((u4 >> 1) & 0x7F7F7F7Fu) + ((*(const uint32_t*)(f + noff + tcol + sub * 4) >> 1) & 0x7F7F7F7Fu);
-                v4 = ((v4 >> 1) & 0x7F7F7F7Fu) + ((*(const uint32_t*)(f + noff + tcol + sub * 4 + 64) >> 1) & 0x7F7F7F7Fu);
+                u = ((u >> 1) & 0x7F7F7F7Fu) + ((un[t] >> 1) & 0x7F7F7F7Fu);
+                v = ((v >> 1) & 0x7F7F7F7Fu) + ((vn[t] >> 1) & 0x7F7F7F7Fu);
             }
-            const uint2 y8 = *(const uint2*)(f + yoff + tcol + sub * 8);
-            uint32_t lum = 0;                                              // carry = last pixel of the previous group, 0 at the start of a blit() call
-            if (!call_start) {
-                const int q = 2 * g - 1;                                   // previous 4-pixel group
-                lum = ((((*(const uint32_t*)(f + yoff + (q >> 2) * EF_TILE + (q & 3) * 4) + dither) & 0xFCFCFCFCu) >> 2) >> 24);
-            }
-            const uint4 o0 = blit_quad(y8.x, dither, chroma_word(tab, u4, v4, vt), chroma_word(tab, u4 >> 8, v4 >> 8, vt), lum);
-            const uint4 o1 = blit_quad(y8.y, dither, chroma_word(tab, u4 >> 16, v4 >> 16, vt), chroma_word(tab, u4 >> 24, v4 >> 24, vt), lum);
+            uint32_t lum = cstart[t] ? 0u : ((((lumw[t] + dither) & 0xFCFCFCFCu) >> 2) >> 24);   // carry = last pixel of the previous group
+#if EF_K2_ARITH
+            const bool vneg = !kNtsc && vt == 512;                         // PAL odd lines: cos_v_neg (video.cpp:584-591)
+            const uint4 o0 = blit_quad(y8[t].x, dither, chroma_word_arith(u, v, vneg), chroma_word_arith(u >> 8, v >> 8, vneg), lum);
+            const uint4 o1 = blit_quad(y8[t].y, dither, chroma_word_arith(u >> 16, v >> 16, vneg), chroma_word_arith(u >> 24, v >> 24, vneg), lum);
+#else
+            const uint4 o0 = blit_quad(y8[t].x, dither, chroma_word(tab, u, v, vt), chroma_word(tab, u >> 8, v >> 8, vt), lum);
+            const uint4 o1 = blit_quad(y8[t].y, dither, chroma_word(tab, u >> 16, v >> 16, vt), chroma_word(tab, u >> 24, v >> 24, vt), lum);
+#endif
             uint8_t* o = sm + row * LS + (G::BLIT + gd * 16) * 2;
             *(uint4*)o = o0;
             *(uint4*)(o + 16) = o1;
         }
     }
-
-    // generic-proxy writes -> async proxy, then one bulk store per line (the field rows of a band are contiguous in HBM)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if ((int)threadIdx.x < nlines) {
-        uint16_t* out = D.fields + (size_t)stream * D.field_stride + (size_t)(line0 + (int)threadIdx.x) * G::W;
-        bulk_store_line(out, sm + (int)threadIdx.x * LS, LB);
+    if (threadIdx.x < 16) {
+        const int l = (int)threadIdx.x;
+        uint16_t* out = out0 + (size_t)l * G::W;
+        const uint8_t* tmpl = sm + (l & 1) * LS;
+        bulk_store(out, tmpl, G::BLIT * 2);
+        bulk_store(out + G::BLIT, sm + l * LS + G::BLIT * 2, 2 * EF_W * 2);
+        bulk_store(out + G::BLIT + 2 * EF_W, tmpl + (G::BLIT + 2 * EF_W) * 2, (G::W - G::BLIT - 2 * EF_W) * 2);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory must stay valid until the engine has read it
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 #else

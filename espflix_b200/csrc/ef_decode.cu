@@ -815,15 +815,23 @@ cudaError_t ef_decode_configure()
 int ef_decode_resident_ctas(int which) { return which == 0 ? g_parse_ctas : g_recon_ctas; }
 
 // parse every slice of picture indices [pic0, pic0 + n_pics) into record pictures 0 .. n_pics-1
-cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, cudaStream_t stream)
+// (grids are persistent - one wave of resident CTAs - but never larger than the work: a one-stream context of the
+// level-1 drop-in launches a handful of CTAs, not 592 that each stage 20 KB of tables first)
+cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, size_t max_slices, cudaStream_t stream)
 {
-    ef_parse_kernel<<<sm_count * g_parse_ctas, kParseThreads, kParseSmemBytes, stream>>>(dev, pic0, n_pics);
+    size_t grid = (size_t)sm_count * g_parse_ctas, need = (max_slices + kParseThreads - 1) / kParseThreads;
+    if (need < 1) need = 1;
+    if (need < grid) grid = need;
+    ef_parse_kernel<<<(unsigned)grid, kParseThreads, kParseSmemBytes, stream>>>(dev, pic0, n_pics);
     return cudaGetLastError();
 }
 
 // rebuild one picture index of every stream from record picture `pic_rel`
-cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, cudaStream_t stream)
+cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, size_t n_slots, cudaStream_t stream)
 {
-    ef_recon_kernel<<<sm_count * g_recon_ctas, kReconWarps * 32, ef_recon_smem_bytes(), stream>>>(dev, pic_rel);
+    size_t grid = (size_t)sm_count * g_recon_ctas, need = (n_slots / 2 + kReconWarps - 1) / kReconWarps;
+    if (need < 1) need = 1;
+    if (need < grid) grid = need;
+    ef_recon_kernel<<<(unsigned)grid, kReconWarps * 32, ef_recon_smem_bytes(), stream>>>(dev, pic_rel);
     return cudaGetLastError();
 }

@@ -187,54 +187,46 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
     }
 }
 
-// exclusive prefix of slices-per-stream for every picture index; single CTA of 1024 threads
+// exclusive prefix of slices-per-stream, one CTA of 1024 threads per picture index (grid = max_pictures); the
+// base of a picture index in the flat work list (sum of the totals before it) is taken in ef_fill_kernel
 __global__ void __launch_bounds__(1024)
 ef_prefix_kernel(EfDev* __restrict__ Dp)
 {
     EfDev& D = *Dp;
     __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry, global_base;
+    __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) global_base = 0;
-    __syncthreads();
+    const int p = blockIdx.x;
     const int pmax = min((int)D.info[0], D.max_pictures);
-    for (int p = 0; p < D.max_pictures; p++) {
-        if (p >= pmax) {
-            if (threadIdx.x == 0) { D.pic_total[p] = 0; D.pic_base[p] = 0; D.cursor[p] = 0; }
-            continue;
-        }
-        if (threadIdx.x == 0) carry = 0;
+    if (p >= pmax) {
+        if (threadIdx.x == 0) { D.pic_total[p] = 0; D.cursor[p] = 0; }
+        return;
+    }
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < D.n_streams; base += 1024) {
+        const int s = base + threadIdx.x;
+        uint32_t v = 0;
+        if (s < D.n_streams && (uint32_t)p < D.n_pics[s]) v = D.pics[(size_t)s * D.max_pictures + p].n_slices;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warp_sum[warp] = x;
         __syncthreads();
-        for (int base = 0; base < D.n_streams; base += 1024) {
-            const int s = base + threadIdx.x;
-            uint32_t v = 0;
-            if (s < D.n_streams && (uint32_t)p < D.n_pics[s]) v = D.pics[(size_t)s * D.max_pictures + p].n_slices;
-            uint32_t x = v;
+        if (warp == 0) {
+            uint32_t t = warp_sum[lane], z = t;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
-            if (lane == 31) warp_sum[warp] = x;
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t t = warp_sum[lane], z = t;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
-                warp_sum[lane] = z - t;                   // exclusive offsets of the warps
-            }
-            __syncthreads();
-            const uint32_t excl = carry + warp_sum[warp] + x - v;
-            if (s < D.n_streams) D.pic_pref[(size_t)p * D.n_streams + s] = excl;
-            __syncthreads();
-            if (threadIdx.x == 1023) carry = excl + v;
-            __syncthreads();
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, z, d); if (lane >= d) z += y; }
+            warp_sum[lane] = z - t;                   // exclusive offsets of the warps
         }
-        if (threadIdx.x == 0) {
-            D.pic_total[p] = carry;
-            D.pic_base[p] = global_base;
-            D.cursor[p] = 0;
-            global_base += carry;
-        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_sum[warp] + x - v;
+        if (s < D.n_streams) D.pic_pref[(size_t)p * D.n_streams + s] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
+    if (threadIdx.x == 0) { D.pic_total[p] = carry; D.cursor[p] = 0; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -243,10 +235,17 @@ ef_fill_kernel(EfDev* __restrict__ Dp)
     EfDev& D = *Dp;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int p = (int)(t / D.n_streams), s = (int)(t % D.n_streams);
-    if (p >= D.max_pictures || (uint32_t)p >= D.n_pics[s]) return;
+    if (p >= D.max_pictures) return;
+    if ((uint32_t)p >= D.n_pics[s]) {
+        if (s == 0) { uint32_t b = 0; for (int q = 0; q < p; q++) b += D.pic_total[q]; D.pic_base[p] = b; }
+        return;
+    }
     const EfPic pic = D.pics[(size_t)s * D.max_pictures + p];
     const uint32_t first = pic.first_slice, seq_idx = pic.seq;
-    const size_t dst = (size_t)D.pic_base[p] + D.pic_pref[(size_t)p * D.n_streams + s];
+    uint32_t pbase = 0;                                      // work lists of consecutive picture indices are contiguous
+    for (int q = 0; q < p; q++) pbase += D.pic_total[q];
+    if (s == 0) D.pic_base[p] = pbase;
+    const size_t dst = (size_t)pbase + D.pic_pref[(size_t)p * D.n_streams + s];
     // picture types other than I are parsed with the P tables (picture() ignores B/D headers but
     // their slices still reach slice(), player.cpp:716, 1292)
     const uint32_t type = pic.type == 1 ? 1u : 2u;
@@ -276,7 +275,8 @@ __device__ __forceinline__ void ts_payload(const uint8_t* d, int& start, int& n)
     if (o < 188) { start = o; n = 188 - o; }
 }
 
-// pass 1: per-packet payload length -> out_len[pkt]; pass 2 (after a device scan): copy
+// pass 1: per-packet payload length; pass 2: exclusive scan of the lengths INSIDE every stream (one CTA per stream,
+// streams are independent) + the stream totals; pass 3: scan of the totals -> ES offset of every stream; pass 4: copy.
 __global__ void ef_ts_len_kernel(const uint8_t* __restrict__ ts, uint64_t n_packets, uint32_t* __restrict__ out_len)
 {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,32 +286,61 @@ __global__ void ef_ts_len_kernel(const uint8_t* __restrict__ ts, uint64_t n_pack
     out_len[k] = (uint32_t)n;
 }
 
-__global__ void ef_ts_copy_kernel(const uint8_t* __restrict__ ts, uint64_t n_packets, const uint64_t* __restrict__ out_off, uint8_t* __restrict__ es)
+// one warp per packet: lanes copy the payload bytes to es_off[stream] + offset inside the stream
+__global__ void ef_ts_copy_kernel(const uint8_t* __restrict__ ts, uint64_t n_packets, const uint32_t* __restrict__ local_off, const uint16_t* __restrict__ pkt_stream,
+                                  const uint64_t* __restrict__ es_off, uint8_t* __restrict__ es)
 {
-    // one warp per packet: lanes copy the payload bytes
     const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (k >= n_packets) return;
     const uint8_t* d = ts + k * 188;
     int start, n;
     ts_payload(d, start, n);
-    uint8_t* dst = es + out_off[k];
+    uint8_t* dst = es + es_off[pkt_stream[k]] + local_off[k];
     for (int i = lane; i < n; i += 32) dst[i] = d[start + i];
 }
 
-// exclusive scan of u32 lengths into u64 offsets, plus per-stream ES offsets: single CTA, sequential over chunks
+// exclusive scan of the payload lengths of ONE stream's packets per CTA (grid = n_streams)
+__global__ void __launch_bounds__(256)
+ef_ts_scan_kernel(const uint32_t* __restrict__ len, const uint64_t* __restrict__ ts_off, uint32_t* __restrict__ local_off, uint16_t* __restrict__ pkt_stream,
+                  uint64_t* __restrict__ stream_total)
+{
+    __shared__ uint32_t warp_sum[8];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, s = blockIdx.x;
+    const uint64_t p0 = ts_off[s] / 188, p1 = ts_off[s + 1] / 188;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = p0; base < p1; base += 256) {
+        const uint64_t k = base + threadIdx.x;
+        const uint32_t v = k < p1 ? len[k] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        uint32_t before = carry;
+        for (int w = 0; w < warp; w++) before += warp_sum[w];
+        if (k < p1) { local_off[k] = before + x - v; pkt_stream[k] = (uint16_t)s; }
+        __syncthreads();
+        if (threadIdx.x == 255) carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stream_total[s] = carry;
+}
+
+// ES offset of every stream = exclusive scan of the stream totals (n_streams <= 65,535: one CTA), zero padding behind the ES
 __global__ void __launch_bounds__(1024)
-ef_ts_scan_kernel(const uint32_t* __restrict__ len, uint64_t n_packets, uint64_t* __restrict__ off,
-                  const uint64_t* __restrict__ ts_off, int n_streams, uint64_t* __restrict__ es_off, uint8_t* __restrict__ es)
+ef_ts_offsets_kernel(const uint64_t* __restrict__ stream_total, int n_streams, uint64_t* __restrict__ es_off, uint8_t* __restrict__ es)
 {
     __shared__ uint64_t warp_sum[32];
     __shared__ uint64_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint64_t base = 0; base < n_packets; base += 1024) {
-        const uint64_t k = base + threadIdx.x;
-        const uint64_t v = k < n_packets ? len[k] : 0;
+    for (int base = 0; base < n_streams; base += 1024) {
+        const int k = base + threadIdx.x;
+        const uint64_t v = k < n_streams ? stream_total[k] : 0;
         uint64_t x = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
@@ -325,16 +354,12 @@ ef_ts_scan_kernel(const uint32_t* __restrict__ len, uint64_t n_packets, uint64_t
         }
         __syncthreads();
         const uint64_t excl = carry + warp_sum[warp] + x - v;
-        if (k < n_packets) off[k] = excl;
+        if (k < n_streams) es_off[k] = excl;
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
+    if (threadIdx.x == 0) es_off[n_streams] = carry;
     // K1's bit reader runs a few bytes past the last slice: zero the 256 bytes behind the elementary stream
     if (threadIdx.x < 256) es[carry + threadIdx.x] = 0;
-    // stream boundaries: ES offset of stream s = offset of its first packet
-    for (int s = threadIdx.x; s <= n_streams; s += 1024) {
-        const uint64_t pk = ts_off[s] / 188;
-        es_off[s] = pk < n_packets ? off[pk] : carry;
-    }
 }

@@ -76,6 +76,14 @@ typedef void (*ef_field_sink)(const uint16_t* field, int line_width, int line_co
 void ef_set_video_pacing(int on, ef_field_sink sink, void* user);
 void ef_video_set_frame_counter(int frame_counter);     // _frame_counter at power-up is 0; tests start elsewhere
 
+// Audio side (video.cpp:957-1020; espflix.ino:73-136). push_audio() collects the SBC bytes the demux routes to it;
+// ef_audio_drain() is the offline audio thread: it decodes everything pushed since video_reset() on the GPU (the
+// reference's decode_audio -> sbc_decoder) and hands every frame not yet delivered to the sink as 128 PCM samples
+// (write_pcm_16(mono, 128, 1)) plus the 256 PDM words pdm_second_order makes of them. Returns the frames delivered.
+typedef void (*ef_audio_sink)(const int16_t* pcm, int n_samples, const uint16_t* pdm, void* user);
+void ef_set_audio_sink(ef_audio_sink sink, void* user);
+int ef_audio_drain();
+
 struct ef_decoder_impl;
 
 class MpegDecoder {

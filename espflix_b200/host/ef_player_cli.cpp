@@ -4,9 +4,12 @@
 // pop_empty -> fill Buffer with <= 8 TS packets -> push_full, decoder thread in run(), frames
 // captured from push_video, final flush_picture(1). Usage: ef_player_cli in.ts out.i420 [field.u16 ntsc]
 //   or, with the offline PTS -> field pacing: ef_player_cli in.ts out.i420 --paced fields.u16 ntsc frame_counter0 max_fields
+//   or, with the audio of the program:        ef_player_cli in.ts out.i420 --audio out.pcm out.pdm
+// Prints {"frames": N, "seconds": S, "frames_per_s": R, ...}: the level-1 drop-in rate of one stream (run() to join).
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -25,6 +28,14 @@ static void on_field(const uint16_t* field, int w, int lines, uint32_t fc, void*
     if (g_n_fields < g_max_fields) g_fields.insert(g_fields.end(), field, field + (size_t)w * lines);
     g_n_fields++;
     g_last_fc = fc;
+}
+
+static std::vector<int16_t> g_pcm;
+static std::vector<uint16_t> g_pdm;
+static void on_audio(const int16_t* pcm, int n, const uint16_t* pdm, void*)
+{
+    g_pcm.insert(g_pcm.end(), pcm, pcm + n);
+    g_pdm.insert(g_pdm.end(), pdm, pdm + 2 * n);
 }
 
 static void on_push(Frame* f, int front, int64_t, int, void*)
@@ -57,9 +68,12 @@ int main(int argc, char** argv)
         g_max_fields = atol(argv[7]);
         ef_set_video_pacing(1, on_field, nullptr);
     }
+    const bool audio = argc >= 6 && !strcmp(argv[3], "--audio");
+    if (audio) ef_set_audio_sink(on_audio, nullptr);
     Frame fb[2];
     fb[0].init(); fb[1].init();
     MpegDecoder dec(&fb[0], &fb[1]);
+    const auto t0 = std::chrono::steady_clock::now();
     std::thread th([&] { dec.run(); });
     size_t pos = 0;
     while (pos + 188 <= ts.size()) {
@@ -77,6 +91,13 @@ int main(int argc, char** argv)
     dec.push_full(b);
     th.join();
     dec.flush_picture(1);
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (audio) {
+        const int nf = ef_audio_drain();
+        FILE* a = fopen(argv[4], "wb"); fwrite(g_pcm.data(), 2, g_pcm.size(), a); fclose(a);
+        a = fopen(argv[5], "wb"); fwrite(g_pdm.data(), 2, g_pdm.size(), a); fclose(a);
+        fprintf(stderr, "audio: %d frames\n", nf);
+    }
     FILE* o = fopen(argv[2], "wb");
     fwrite(g_out.data(), 1, g_out.size(), o);
     fclose(o);
@@ -87,10 +108,10 @@ int main(int argc, char** argv)
         FILE* ff = fopen(argv[4], "wb");
         fwrite(g_fields.data(), 2, g_fields.size(), ff);
         fclose(ff);
-        printf("{\"frames\": %ld, \"fields\": %ld}\n", g_frames, g_n_fields);
+        printf("{\"frames\": %ld, \"fields\": %ld, \"seconds\": %.6f}\n", g_frames, g_n_fields, secs);
         return 0;
     }
-    if (argc >= 5) {                               // one field of the last presented frame through video_isr
+    if (argc >= 5 && !audio) {                     // one field of the last presented frame through video_isr
         const int ntsc = atoi(argv[4]);
         video_init(ntsc);
         const int w = ntsc ? 912 : 1136, lines = ntsc ? 262 : 312;
@@ -100,6 +121,6 @@ int main(int argc, char** argv)
         fwrite(field.data(), 2, field.size(), ff);
         fclose(ff);
     }
-    printf("{\"frames\": %ld}\n", g_frames);
+    printf("{\"frames\": %ld, \"seconds\": %.6f, \"frames_per_s\": %.1f, \"audio_frames\": %zu}\n", g_frames, secs, g_frames / secs, g_pcm.size() / 128);
     return 0;
 }

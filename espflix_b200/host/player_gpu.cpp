@@ -1,7 +1,11 @@
 // espflix_b200/host/player_gpu.cpp — MpegDecoder/Frame (reference: src/player.cpp) on top of the
-// C-ABI. The host keeps only the transport side: Buffer queues, TS/PES demux of the video PID
-// (more()/demux(), player.cpp:381-493), access-unit cutting and the push_video/buffer-swap protocol
-// of flush_picture() (player.cpp:692). Every picture is decoded by the CUDA kernels.
+// C-ABI. The host keeps only the transport side: Buffer queues, TS/PES demux (more()/demux(),
+// player.cpp:381-493: video PID into the access-unit cutter, audio PIDs to push_audio with the reference's
+// "no PTS mutes the stream" state), and the push_video/buffer-swap protocol of flush_picture() (player.cpp:692).
+// Every picture is decoded by the CUDA kernels, and not one by one: complete access units are collected and a whole
+// batch (kBatchPictures) goes through ONE ef_submit_es_host -> ef_index -> ef_decode_all_to_host; the callbacks
+// then fire in the reference's order with the reference's Frame contents (the decoder runs ahead of presentation
+// by at most one batch, as the reference's decoder thread runs ahead of its display by one frame).
 #include "ef_player.h"
 
 #include <stdio.h>
@@ -52,15 +56,21 @@ int64_t pes_timestamp(const uint8_t* d, int flags)       // parse_pts, player.cp
 }
 }  // namespace
 
+constexpr int kBatchPictures = 32;             // access units per GPU submit
+constexpr size_t kBatchBytes = 768 << 10;       // ... or this much elementary stream, whichever comes first (es_capacity is 1 MB)
+
 struct ef_decoder_impl {
     ef_ctx* ctx = nullptr;
     BufferQueue full, empty;
     Buffer pool[4];
     std::vector<uint8_t> es;                   // video ES not yet decoded
     std::vector<std::pair<size_t, int64_t>> pes;   // (offset in es, pts) of PES headers seen
-    std::vector<uint8_t> staging;
+    std::vector<size_t> unit_end;              // complete access units at the front of `es`: end offsets
+    std::vector<int64_t> unit_pts;             // PTS latched by the picture header of each unit (-1: keep)
+    uint8_t* frames = nullptr;                 // pinned: kBatchPictures decoded pictures in the strip layout
     bool in_picture = false;                   // a picture start code has been seen in `es`
-    size_t scan_from = 0;
+    size_t scan_from = 0, unit_start = 0;
+    int64_t audio_pts = -1;                    // _audio_pts (player.cpp:418-431)
 };
 
 MpegDecoder::MpegDecoder(Frame* fb0, Frame* fb1)
@@ -73,18 +83,18 @@ MpegDecoder::MpegDecoder(Frame* fb0, Frame* fb1)
     _impl = new ef_decoder_impl();
     ef_config cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.device = 0; cfg.n_streams = 1; cfg.max_pictures = 4; cfg.max_slices_per_picture = 64;
+    cfg.device = 0; cfg.n_streams = 1; cfg.max_pictures = kBatchPictures; cfg.max_slices_per_picture = 64;
     cfg.es_capacity = 1 << 20; cfg.fields = 0;
-    if (ef_create(&_impl->ctx, &cfg) != EF_OK) {
+    if (ef_create(&_impl->ctx, &cfg) != EF_OK || ef_host_alloc((void**)&_impl->frames, (size_t)kBatchPictures * EF_FRAME_BYTES) != EF_OK) {
         fprintf(stderr, "MpegDecoder: %s\n", ef_last_error());   // no CPU decoder to fall back to
         abort();
     }
-    _impl->staging.resize(EF_FRAME_BYTES);
     for (int i = 0; i < 4; i++) _impl->empty.push(&_impl->pool[i]);
 }
 
 MpegDecoder::~MpegDecoder()
 {
+    ef_host_free(_impl->frames);
     ef_destroy(_impl->ctx);
     delete _impl;
 }
@@ -96,8 +106,8 @@ int64_t MpegDecoder::get_pts() { return _last_pts; }
 void MpegDecoder::reset()                       // player.cpp:439
 {
     _impl->full.drain_into(_impl->empty);
-    _impl->es.clear(); _impl->pes.clear();
-    _impl->in_picture = false; _impl->scan_from = 0;
+    _impl->es.clear(); _impl->pes.clear(); _impl->unit_end.clear(); _impl->unit_pts.clear();
+    _impl->in_picture = false; _impl->scan_from = 0; _impl->unit_start = 0; _impl->audio_pts = -1;
     ef_reset(_impl->ctx);
     _fb_index = 0;
     _reference = _fb[_fb_index++ & 1];
@@ -116,58 +126,75 @@ void MpegDecoder::flush_picture(int mode)       // player.cpp:692
     if (!mode) _last_pts = _pts;
 }
 
-// decode one access unit (headers + exactly one picture) and land it in the host Frame _current
-static void decode_unit(MpegDecoder* d, ef_decoder_impl* im, const uint8_t* p, size_t n)
+// Decode the collected access units in ONE submit and replay the reference's per-picture protocol: at a picture
+// header the decoder latches the PTS, presents the previous picture (flush_picture, player.cpp:692-702) and swaps
+// buffers; the slices then fill _current.
+static void decode_batch(MpegDecoder* d, ef_decoder_impl* im)
 {
-    const uint64_t off[2] = { 0, (uint64_t)n };
-    int rc = ef_submit_es_host(im->ctx, p, off, nullptr);
+    const int n = (int)im->unit_end.size();
+    if (!n) return;
+    const size_t bytes = im->unit_end.back();
+    const uint64_t off[2] = { 0, (uint64_t)bytes };
+    int rc = ef_submit_es_host(im->ctx, im->es.data(), off, nullptr);
     if (rc == EF_OK) rc = ef_index(im->ctx, nullptr);
-    if (rc == EF_OK) rc = ef_decode_picture(im->ctx, 0, nullptr);
-    if (rc == EF_OK) rc = ef_read_frame(im->ctx, 0, d->_fb_index & 1, im->staging.data());
-    if (rc != EF_OK) { fprintf(stderr, "MpegDecoder: %s\n", ef_last_error()); return; }   // reference convention: print and keep going
-    Frame* f = d->_current;
-    for (int s = 0; s < FB_SLICES; s++) memcpy(f->_slices[s], im->staging.data() + (size_t)s * EF_STRIP_BYTES, EF_STRIP_BYTES);
+    if (rc == EF_OK) rc = ef_decode_all_to_host(im->ctx, n, im->frames, 1, nullptr);
+    if (rc == EF_OK) rc = ef_sync(im->ctx, nullptr);
+    if (rc != EF_OK) fprintf(stderr, "MpegDecoder: %s\n", ef_last_error());   // reference convention: print and keep going
+    for (int k = 0; k < n; k++) {
+        if (im->unit_pts[k] != -1) d->_pts = im->unit_pts[k];
+        d->flush_picture(0);
+        if (rc == EF_OK) {
+            const uint8_t* src = im->frames + (size_t)k * EF_FRAME_BYTES;
+            Frame* f = d->_current;
+            for (int s = 0; s < FB_SLICES; s++) memcpy(f->_slices[s], src + (size_t)s * EF_STRIP_BYTES, EF_STRIP_BYTES);
+        }
+    }
+    // drop what has been decoded, keep PES marks and scan positions relative to the new origin
+    im->es.erase(im->es.begin(), im->es.begin() + (long)bytes);
+    std::vector<std::pair<size_t, int64_t>> keep;
+    for (auto& pp : im->pes) if (pp.first >= bytes) keep.push_back({ pp.first - bytes, pp.second });
+    im->pes.swap(keep);
+    im->unit_end.clear(); im->unit_pts.clear();
+    im->scan_from -= bytes; im->unit_start -= bytes;
 }
 
-// cut complete access units off the front of `es`: a unit ends where, after a picture start code,
-// the next sequence / GOP / picture / sequence-end start code begins (marker(), player.cpp:1318)
+// cut complete access units off `es`: a unit ends where, after a picture start code, the next sequence / GOP /
+// picture / sequence-end start code begins (marker(), player.cpp:1318)
 static void drain(MpegDecoder* d, ef_decoder_impl* im, bool final)
 {
     std::vector<uint8_t>& es = im->es;
-    size_t unit_start = 0, i = im->scan_from;
+    size_t i = im->scan_from;
     while (i + 4 <= es.size()) {
         if (es[i] != 0 || es[i + 1] != 0 || es[i + 2] != 1) { i++; continue; }
         const uint8_t code = es[i + 3];
         const bool header = code == 0x00 || code == 0xB3 || code == 0xB8 || code == 0xB7;
         if (header && im->in_picture) {
-            decode_unit(d, im, es.data() + unit_start, i - unit_start);
-            unit_start = i;
+            im->unit_end.push_back(i);
+            im->unit_start = i;
             im->in_picture = false;
         }
-        if (code == 0x00) {                                       // picture(): present the previous one, swap, latch the PTS
-            int64_t pts = d->_pts;
+        if (code == 0x00) {                                       // picture(): the PTS of the PES this header lies in
+            int64_t pts = -1;
             for (auto& pp : im->pes) if (pp.first <= i + 3) pts = pp.second;
-            if (pts != -1) d->_pts = pts;
-            d->flush_picture(0);
+            im->unit_pts.push_back(pts);
             im->in_picture = true;
         }
         i += 4;
     }
-    if (final && im->in_picture && es.size() > unit_start) {
-        decode_unit(d, im, es.data() + unit_start, es.size() - unit_start);
-        unit_start = es.size();
+    im->scan_from = i;                     // everything before i has been examined; a start code straddling the next Buffer starts at or after i
+    if (final && im->in_picture && es.size() > im->unit_start) {
+        im->unit_end.push_back(es.size());
+        im->unit_start = es.size();
         im->in_picture = false;
-        i = es.size();
+        im->scan_from = es.size();
     }
-    // drop what has been decoded, keep PES marks relative to the new origin
-    if (unit_start) {
-        es.erase(es.begin(), es.begin() + (long)unit_start);
-        std::vector<std::pair<size_t, int64_t>> keep;
-        for (auto& pp : im->pes) if (pp.first >= unit_start) keep.push_back({ pp.first - unit_start, pp.second });
-        im->pes.swap(keep);
+    if (final || (int)im->unit_end.size() >= kBatchPictures || (!im->unit_end.empty() && es.size() >= kBatchBytes)) {
+        // a picture header already seen beyond the last complete unit keeps its latched PTS for the next batch
+        std::vector<int64_t> carry(im->unit_pts.begin() + (long)im->unit_end.size(), im->unit_pts.end());
+        im->unit_pts.resize(im->unit_end.size());
+        decode_batch(d, im);
+        im->unit_pts = carry;
     }
-    im->scan_from = i >= unit_start ? i - unit_start : 0;   // everything before i has been examined; a start code
-                                                            // straddling the next Buffer starts at or after i
 }
 
 void MpegDecoder::run()                          // player.cpp:1355
@@ -201,7 +228,8 @@ void MpegDecoder::run()                          // player.cpp:1355
                 if (pus) im->pes.push_back({ im->es.size(), pts });
                 if (payload < end) im->es.insert(im->es.end(), payload, end);
             } else if (pid == 0x101 || pid == 0x102) {
-                if (payload < end) push_audio(payload, (int)(end - payload), pts, false);
+                if (pus) im->audio_pts = pts;    // a PES without a (well-formed) PTS mutes the stream until the next one with (player.cpp:418-431)
+                if (im->audio_pts != -1 && payload < end) push_audio(payload, (int)(end - payload), pts, false);
             }
         }
         im->empty.push(b);

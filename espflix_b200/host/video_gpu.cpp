@@ -67,12 +67,48 @@ void video_init(int ntsc)                         // video.cpp:572
     _line_counter = 0;
 }
 
+// ---- audio (video.cpp:957-1020, espflix.ino:73-136) ---------------------------------------------------------------
+// push_audio() feeds a ring that the reference's audio thread drains frame by frame (decode_audio -> sbc_decoder ->
+// write_pcm_16 -> pdm_second_order). Here the bytes are collected and ef_audio_drain() - the offline audio thread -
+// decodes everything pushed since video_reset() in one batched GPU call and hands the frames not delivered yet to
+// the sink, 128 PCM samples and 256 PDM words each, in order.
+namespace {
+std::vector<uint8_t> g_sbc;
+size_t g_audio_delivered = 0;                  // frames already handed to the sink
+ef_audio_sink g_audio_sink = nullptr;
+void* g_audio_user = nullptr;
+}  // namespace
+
+void ef_set_audio_sink(ef_audio_sink sink, void* user) { g_audio_sink = sink; g_audio_user = user; }
+
+void push_audio(const uint8_t* data, int len, int64_t, bool)   // video.cpp:1007
+{
+    if (len > 0) g_sbc.insert(g_sbc.end(), data, data + len);
+}
+
+int ef_audio_drain()
+{
+    if (g_sbc.empty()) return 0;
+    const uint64_t off[2] = { 0, (uint64_t)g_sbc.size() };
+    ef_audio_info info;
+    if (ef_audio_decode(0, g_sbc.data(), off, 1, &info, nullptr, 0, nullptr) != EF_OK) { fprintf(stderr, "audio: %s\n", ef_last_error()); return 0; }
+    if (info.frame_size <= 0 || info.n_frames <= g_audio_delivered) return 0;
+    std::vector<int16_t> pcm((size_t)info.n_frames * 128);
+    std::vector<uint16_t> pdm((size_t)info.n_frames * 256);
+    if (ef_audio_decode(0, g_sbc.data(), off, 1, &info, pcm.data(), pcm.size(), pdm.data()) != EF_OK) { fprintf(stderr, "audio: %s\n", ef_last_error()); return 0; }
+    int n = 0;
+    for (size_t k = g_audio_delivered; k < info.n_frames; k++, n++)
+        if (g_audio_sink) g_audio_sink(pcm.data() + k * 128, 128, pdm.data() + k * 256, g_audio_user);   // write_pcm_16(mono, 128, 1)
+    g_audio_delivered = info.n_frames;
+    return n;
+}
+
 void video_reset()                                  // video.cpp:1070
 {
     _pts_origin = _video_frame_counter_origin = _video_pts = 0;
+    g_sbc.clear(); g_audio_delivered = 0;          // _sbc_r = _sbc_w = _sbc_frame_size = 0
 }
 void video_pause(int) {}
-void push_audio(const uint8_t*, int, int64_t, bool) {}   // audio side-chain is out of scope
 
 void push_video(Frame* f, int front, int64_t pts, int mode)   // video.cpp:1023
 {

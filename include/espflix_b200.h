@@ -38,6 +38,9 @@
  *   ef_video_set_scroll / _overlay  _hscroll video.cpp:1146-1154, composite() video.cpp:839-887
  *   ef_tsidx_scan                 make_index(const string&, vector<idx>&) indexer/indexer.cpp:90
  *   ef_tsidx_samples              pts2seq(idx&,int,int) + pts2pos indexer/indexer.cpp:193-228
+ *   ef_audio_demux_ts             MpegDecoder::demux() for the audio PIDs -> push_audio() player.cpp:381-432, video.cpp:1007
+ *   ef_audio_decode               decode_audio() video.cpp:964, sbc_decoder() sbc_decoder.cpp:343, pdm_second_order()
+ *                                 espflix.ino:73
  * Calls run on the context's device and restore the caller's current device.
  */
 #ifndef ESPFLIX_B200_H
@@ -110,9 +113,10 @@ int ef_decode_picture(ef_ctx* ctx, int pic, void* stream);
 int ef_decode_all(ef_ctx* ctx, int n_pictures, void* stream);
 /* The same, handing EVERY picture to the host the way the reference's decoder hands every picture to push_video()
  * (video.h:49; player.cpp:692-702): after the K1b launch of picture index p the batch is exported as I420 and copied
- * to dst[p][stream] (n_pictures x n_streams x EF_I420_BYTES, should be pinned) on the context's read-back stream
- * while picture index p + 1 is rebuilt. Complete after ef_sync. Streams with fewer pictures repeat stale data. */
-int ef_decode_all_to_host(ef_ctx* ctx, int n_pictures, uint8_t* dst, void* stream);
+ * to dst[p][stream] (n_pictures x n_streams x EF_FRAME_BYTES, should be pinned) on the context's read-back stream
+ * while picture index p + 1 is rebuilt. layout 0 = I420, 1 = the reference's strips (video.h:36-44). Complete after
+ * ef_sync. Streams with fewer pictures repeat stale data. */
+int ef_decode_all_to_host(ef_ctx* ctx, int n_pictures, uint8_t* dst, int layout, void* stream);
 
 /* Frame stores. fb = 0/1 is the reference's _fb[] index; -1 = the frame holding the most recently
  * decoded picture of that stream (what the next push_video would present). Synchronous. */
@@ -152,6 +156,11 @@ int ef_video_isr(ef_ctx* ctx, int stream_index, int line, uint16_t* buf /* line_
 /* blit(): width luma pixels starting at x of line (0..191) -> 2*width samples at dst (host). */
 int ef_blit(ef_ctx* ctx, int stream_index, int fb, uint16_t* dst, int line, int x, int width, int frame_counter);
 
+/* Pinned host memory for the asynchronous entry points (ef_submit_es_host, ef_read_latest_i420_async,
+ * ef_decode_all_to_host) for callers that do not link the CUDA runtime themselves; the counterpart of the Buffers and
+ * Frames the reference's decoder allocates for its caller (player.cpp:367-368; Frame::init player.cpp:25). */
+int ef_host_alloc(void** ptr, size_t bytes);
+void ef_host_free(void* ptr);
 /* Launch counter: kernels this library has launched since ef_create (bench.py "gpu_launches"). */
 uint64_t ef_launch_count(ef_ctx* ctx);
 /* Stage timing, the counterpart of the reference's MEASURE() tick counters (player.cpp:1001, streamer.h): with
@@ -176,6 +185,35 @@ int ef_tsidx_scan(int device, const uint8_t* ts, const uint64_t* off, int n_file
                   ef_tsidx_info* info, int64_t* seq_pts, uint32_t* seq_pos);
 int ef_tsidx_samples(int device, const int64_t* seq_pts, const uint32_t* seq_pos, int n_seq, int64_t first_pts, int64_t last_pts,
                      uint32_t bin_size, uint32_t* samples, uint32_t cap, uint32_t* n_samples);
+
+/* ---- audio: the SBC decoder and the PDM modulator of the reference, batched ---------------------
+ * Stateless (no context); host buffers; the kernels run on `device`.
+ * ef_audio_demux_ts  MpegDecoder::demux() for PID 0x101 / 0x102 (src/player.cpp:381-432): the payload bytes that reach
+ *                    push_audio() (video.cpp:1007) for n_files transport streams packed back to back (off[n_files + 1],
+ *                    multiples of 188). A PES that starts without a (well-formed) PTS mutes its stream until the next
+ *                    PES that has one. es_off[n_files + 1] receives the byte offsets of every file's audio in `es`.
+ * ef_audio_decode    decode_audio() (video.cpp:964-986) + sbc_decoder() (sbc_decoder.cpp:343) + pdm_second_order()
+ *                    (espflix.ino:73) for n_streams SBC byte streams (off[n_streams + 1]): the frame size is learned
+ *                    from the first frame (which the reference decodes twice), whole frames are decoded in order to 128
+ *                    int16 samples each at pcm + info[s].pcm_offset, and - when pdm is not NULL - every sample becomes
+ *                    2 x 16 one-bit samples at pdm + 2 * pcm_offset (modulator state zero at the start of a stream).
+ *                    pcm == NULL: sizing call, only info[] is filled. info[s].frame_size: > 0 bytes, 0 empty stream,
+ *                    -1 first frame rejected by the reference (nothing decoded), -2 outside its domain (the reference
+ *                    handles mono, 8 subbands, 16 blocks only). */
+typedef struct { int32_t frame_size; uint32_t n_frames; uint64_t pcm_offset; } ef_audio_info;
+int ef_audio_demux_ts(int device, const uint8_t* ts, const uint64_t* off, int n_files, uint8_t* es, uint64_t es_cap, uint64_t* es_off);
+int ef_audio_decode(int device, const uint8_t* sbc, const uint64_t* off, int n_streams, ef_audio_info* info,
+                    int16_t* pcm, uint64_t pcm_cap, uint16_t* pdm);
+
+/* ---- experiment, NOT on the decode path (north_star: "the 8x8 IDCT ... batched onto tcgen05 tensor cores") ------------
+ * The linearised IDCT of MpegDecoder::idct() (player.cpp:922-996) as a [n_blocks x 64] x [64 x 64] TF32 GEMM on
+ * tcgen05.mma with a TMEM accumulator and TMA-fed operand tiles (csrc/ef_idct_tc.cu). coefs: n_blocks x 64 prescaled
+ * int32 coefficients as idct() receives them; L: the 64 x 64 linear map (row = output sample, column = input
+ * coefficient; tests/idct_linear.py derives it from the butterfly); out: n_blocks x 64 rounded residuals. The reference
+ * transform rounds inside every butterfly, so this differs from it by up to +-1 (tests/test_idct_tc_gpu.py measures how
+ * often) and cannot replace the integer kernel where YUV must be bit-exact. prep_ms / mma_ms: best-of-`repeats` device
+ * times of the operand pre-pass and of the MMA kernel. */
+int ef_idct_tc_run(int device, const int32_t* coefs, int n_blocks, const double* L, int32_t* out, float* prep_ms, float* mma_ms, int repeats);
 
 #ifdef __cplusplus
 }

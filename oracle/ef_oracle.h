@@ -111,7 +111,7 @@ size_t efo_build_idx(const uint8_t* const ts[3], const size_t len[3], uint8_t* o
  *                     (stores <= cap_samples), -2 outside the domain
  * efo_pdm             pdm_second_order (espflix.ino:73-107) from reset state: 2 n words of 16 one-bit samples */
 size_t efo_demux_audio_ts(const uint8_t* ts, size_t len, uint8_t* es, size_t cap);
-int efo_sbc_frame(const uint8_t* data, int len, int32_t sb_sample[16][8]);
+int efo_sbc_frame(const uint8_t* data, size_t len, int32_t sb_sample[16][8]);
 long efo_sbc_decode(const uint8_t* es, size_t len, int16_t* pcm, size_t cap_samples);
 void efo_pdm(const int16_t* pcm, size_t n, uint16_t* out);
 

@@ -20,14 +20,14 @@
 
 static int be16a(const uint8_t* p) { return (p[0] << 8) | p[1]; }
 
-/* parse_pts presence only matters here: demux() keeps pushing audio while _audio_pts != -1 (player.cpp:418-431) */
+/* parse_pts (player.cpp:299): a malformed marker nibble reads as -1, which mutes the audio like a missing PTS */
 static int64_t pes_pts_a(const uint8_t* d, int flags)
 {
-    (void)flags;
-    int64_t pts = (int64_t)((d[0] >> 1) & 7) << 30;
-    pts |= (int64_t)(be16a(d + 1) >> 1) << 15;
-    pts |= (int64_t)(be16a(d + 3) >> 1);
-    return pts;
+    flags = (flags >> 2) & 0x30;
+    if ((d[0] & 0xF0) != flags) return -1;
+    int64_t n = ((int64_t)(d[0] & 0x0E)) << 29;
+    n += (int64_t)(be16a(d + 1) >> 1) << 15;
+    return n + (be16a(d + 3) >> 1);
 }
 
 size_t efo_demux_audio_ts(const uint8_t* ts, size_t len, uint8_t* es, size_t cap)
@@ -36,7 +36,7 @@ size_t efo_demux_audio_ts(const uint8_t* ts, size_t len, uint8_t* es, size_t cap
     int64_t audio_pts = -1;                                    /* MpegDecoder::reset(), player.cpp:449 */
     for (size_t pos = 0; pos + 188 <= len; pos += 188) {
         const uint8_t* d = ts + pos;
-        if (d[0] != 0x47) break;                               /* "ts lost sync" (player.cpp:477) */
+        if (d[0] != 0x47) continue;                            /* "ts lost sync": more() drops the packet and goes on (player.cpp:476-479) */
         int pid = ((d[1] << 8) + d[2]) & 0x1fff;
         const uint8_t* data = d + 4;
         if (d[3] & 0x20) data = d + 5 + d[4];
@@ -101,7 +101,7 @@ static void bit_allocation8(int frequency, int allocation, int bitpool, const ui
         if (bits[sb] < 16) { bits[sb]++; bitcount++; }
 }
 
-int efo_sbc_frame(const uint8_t* data, int len, int32_t sb_sample[16][8])
+int efo_sbc_frame(const uint8_t* data, size_t len, int32_t sb_sample[16][8])
 {
     if (len < 4 || data[0] != 0x9C) return -1;
     const int frequency = (data[1] >> 6) & 3, blocks = 4 * (((data[1] >> 4) & 3) + 1), mode = (data[1] >> 2) & 3;
@@ -109,7 +109,7 @@ int efo_sbc_frame(const uint8_t* data, int len, int32_t sb_sample[16][8])
     if (mode == 3 || subbands == 4) return -1;
     if (mode != 0 || blocks != 16) return -2;                  /* outside the reference's own domain (see the header comment) */
     uint8_t sf[8];
-    for (int sb = 0; sb < 8; sb += 2) { sf[sb] = data[4 + (sb >> 1)] >> 4; sf[sb + 1] = data[4 + (sb >> 1)] & 15; }
+    for (int sb = 0; sb < 8; sb += 2) { uint8_t a = 4 + (size_t)(sb >> 1) < len ? data[4 + (sb >> 1)] : 0; sf[sb] = a >> 4; sf[sb + 1] = a & 15; }
     int bits[8];
     bit_allocation8(frequency, allocation, bitpool, sf, bits);
     const uint8_t* p = data + 8;
@@ -120,7 +120,7 @@ int efo_sbc_frame(const uint8_t* data, int len, int32_t sb_sample[16][8])
             int32_t sample = 0;
             const int level = bits[sb];
             if (level) {
-                while (have < level) { acc = (acc << 8) | *p++; have += 8; }
+                while (have < level) { acc = (acc << 8) | (p < data + len ? *p : 0); p++; have += 8; }   /* bytes behind the stream read as 0 */
                 have -= level;
                 uint32_t raw = (acc >> have) & ((1u << level) - 1);
                 /* IQUANT (sbc_decoder.cpp:262): ((2 raw + 1) << scale) / (2^level - 1), then minus 2^scale; 32-bit wrap as compiled */
@@ -175,16 +175,13 @@ long efo_sbc_decode(const uint8_t* es, size_t len, int16_t* pcm, size_t cap_samp
     int32_t sb[16][8];
     memset(sb, 0, sizeof(sb));
     int16_t scratch[8];
-    uint8_t probe[64];
-    memset(probe, 0, sizeof(probe));
-    memcpy(probe, es, len < 64 ? len : 64);
-    int frame_size = efo_sbc_frame(probe, 64, sb);
+    int frame_size = efo_sbc_frame(es, len, sb);               /* the probe: sbc_decoder(&_sbc, _sbc_buf, 64, ...) reads what it needs from the ring */
     if (frame_size == -2) return -2;
     for (int blk = 0; blk < 16; blk++) efo_sbc_synth(&st, sb[blk], scratch);
     if (frame_size <= 0) return frame_size == 0 ? 0 : -1;      /* the reference stalls / misbehaves here: outside the domain */
     long n = 0;
     for (size_t r = 0; r + (size_t)frame_size <= len; r += (size_t)frame_size) {
-        int fs = efo_sbc_frame(es + r, frame_size, sb);        /* a rejected frame leaves sb[] as it was */
+        int fs = efo_sbc_frame(es + r, len - r, sb);           /* a rejected frame leaves sb[] as it was */
         if (fs == -2) return -2;
         for (int blk = 0; blk < 16; blk++) {
             int16_t out[8];

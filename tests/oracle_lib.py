@@ -56,7 +56,33 @@ class Oracle:
         L.efo_pts2seq.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, VP, ctypes.c_int]
         L.efo_build_idx.restype = ctypes.c_size_t
         L.efo_build_idx.argtypes = [VP, VP, VP, ctypes.c_size_t]
+        L.efo_demux_audio_ts.restype = ctypes.c_size_t
+        L.efo_demux_audio_ts.argtypes = [VP, ctypes.c_size_t, VP, ctypes.c_size_t]
+        L.efo_sbc_decode.restype = ctypes.c_long
+        L.efo_sbc_decode.argtypes = [VP, ctypes.c_size_t, VP, ctypes.c_size_t]
+        L.efo_pdm.argtypes = [VP, ctypes.c_size_t, VP]
         self._video = {}
+
+    # -- audio (oracle/ef_oracle_audio.c) --------------------------------------------------------------
+    def demux_audio_ts(self, ts):
+        ts = np.ascontiguousarray(np.frombuffer(bytes(ts), dtype=np.uint8))
+        es = np.empty(ts.size + 16, dtype=np.uint8)
+        n = self.lib.efo_demux_audio_ts(ts.ctypes.data, ts.size, es.ctypes.data, es.size)
+        return es[:n].copy()
+
+    def sbc_decode(self, es):
+        """-> PCM int16 array, or the negative code of efo_sbc_decode"""
+        es = np.ascontiguousarray(np.frombuffer(bytes(es), dtype=np.uint8))
+        cap = (es.size // 8 + 2) * 128
+        pcm = np.zeros(cap, dtype=np.int16)
+        n = self.lib.efo_sbc_decode(es.ctypes.data if es.size else pcm.ctypes.data, es.size, pcm.ctypes.data, cap)
+        return int(n) if n < 0 else pcm[:n].copy()
+
+    def pdm(self, pcm):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        out = np.zeros(2 * pcm.size, dtype=np.uint16)
+        self.lib.efo_pdm(pcm.ctypes.data, pcm.size, out.ctypes.data)
+        return out
 
     def demux_ts(self, ts):
         ts = np.ascontiguousarray(np.frombuffer(bytes(ts), dtype=np.uint8))

@@ -77,3 +77,24 @@ def test_mirrored_presentation_pacing(name, tmp_path):
     stream = np.fromfile(fields, dtype=np.uint16)
     assert stream.nbytes == p["stream_bytes"]
     assert hashlib.sha256(stream.tobytes()).hexdigest() == p["stream_sha256"]
+
+
+@pytest.mark.parametrize("name", ["splash", "vmedia"])
+def test_mirrored_program_with_audio(name, tmp_path, oracle):
+    """A whole TS program through the mirror: pictures via push_video (batched decode underneath), the SBC audio of
+    PID 0x101/0x102 via push_audio -> ef_audio_drain (the offline audio thread) -> sink: PCM and PDM equal the pins
+    the unmodified reference produced, and the CLI reports the level-1 drop-in rate of one stream."""
+    vp = json.load(open(os.path.join(G, "decode_pins.json")))[name]
+    ap = json.load(open(os.path.join(G, "audio_pins.json")))[name]
+    out, pcm_p, pdm_p = [os.path.join(str(tmp_path), n) for n in ("out.i420", "a.pcm", "a.pdm")]
+    r = subprocess.run([ef_build.HOST_CLI, os.path.join(G, name + ".ts"), out, "--audio", pcm_p, pdm_p], capture_output=True, timeout=600, check=True)
+    info = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    frames = np.fromfile(out, dtype=np.uint8)
+    assert info["frames"] == vp["frames"] and hashlib.sha256(frames.tobytes()).hexdigest() == vp["i420_sha256"]
+    assert info["frames_per_s"] > 0 and info["audio_frames"] == ap["n_frames"]
+    pcm, pdm = np.fromfile(pcm_p, dtype=np.int16), np.fromfile(pdm_p, dtype=np.uint16)
+    for a, b in ap["undefined"]:
+        pcm[a:b] = 0
+    assert hashlib.sha256(pcm.tobytes()).hexdigest() == ap["pcm_sha256_masked"]
+    assert hashlib.sha256(pdm[:ap["pdm_defined_words"]].tobytes()).hexdigest() == ap["pdm_sha256_defined"]
+    print("level-1 drop-in, %s: %.0f frames/s (one stream, %d pictures)" % (name, info["frames_per_s"], info["frames"]))

@@ -59,3 +59,28 @@ def test_numeric_tables():
     import math
     s = [1.0] + [math.sqrt(2) * math.cos(k * math.pi / 16) for k in range(1, 8)]
     assert _u8("ef_aan_prescale") == [int(math.floor(32 * s[i] * s[j] + 0.5)) for i in range(8) for j in range(8)]
+
+
+def test_chroma_lut_closed_form():
+    """The composite chroma LUTs (video.cpp:335-507; derivation espflix.cpp:1091-1180) have a closed form, used by K2's
+    EF_K2_ARITH variant (csrc/ef_composite.cu chroma_r / chroma_word_arith): phases 48, 48 +- r(c), r(c) = sgn(128 - c) *
+    ((16 |128 - c| + 11) / 22), clamped to [0, 127]; and the kernel's multiply-shift division is exact on its range."""
+    import numpy as np
+    assert all((x * 745) >> 14 == x // 22 for x in range(0, 2060))
+
+    def r(c):
+        d = 128 - c
+        q = (16 * abs(d) + 11) // 22
+        return q if d >= 0 else -q
+
+    def cl(x):
+        return max(0, min(127, x))
+
+    for name in ("ntsc", "pal"):
+        t = np.fromfile(os.path.join(ROOT, "tests", "golden", "color_tab_%s.u32" % name), dtype=np.uint32)
+        for c in range(256):
+            rr = r(c)
+            sin = (48 << 24) | (48 << 16) | (cl(48 + rr) << 8) | cl(48 - rr)
+            cos = (cl(48 + rr) << 24) | (cl(48 - rr) << 16) | (48 << 8) | 48
+            cosn = (cl(48 - rr) << 24) | (cl(48 + rr) << 16) | (48 << 8) | 48
+            assert t[c] == sin and t[256 + c] == cos and t[512 + c] == (cos if name == "ntsc" else cosn), (name, c)
