@@ -220,16 +220,19 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
                     cfg->n_streams, cfg->max_pictures, cfg->max_slices_per_picture, cfg->es_capacity);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev <= cfg->device)
+    if (e != cudaSuccess || cfg->device < 0 || ndev <= cfg->device)
         return fail(EF_ECUDA, "no usable CUDA device %d (%s); this library has no CPU path", cfg->device, cudaGetErrorString(e));
     DeviceScope scope_(cfg->device);
     ef_ctx* c = new ef_ctx();
     c->cfg = *cfg;
+    struct Guard {                                // every failure path below releases what has been created so far
+        ef_ctx* c;
+        ~Guard() { if (c) ef_destroy(c); }
+    } guard{ c };
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     c->sm_count = prop.multiProcessorCount;
     if ((size_t)prop.sharedMemPerBlockOptin < ef_recon_smem_bytes()) {
-        delete c;
         return fail(EF_ECUDA, "device offers %zu B shared memory per CTA, kernel needs %zu", (size_t)prop.sharedMemPerBlockOptin, ef_recon_smem_bytes());
     }
     CK(ef_decode_configure());
@@ -243,7 +246,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     h.max_slices = cfg->max_pictures * cfg->max_slices_per_picture;
     h.max_seq = cfg->max_pictures;
     int rc;
-#define A(ptr, count) if ((rc = dev_alloc(c, &(ptr), (count))) != EF_OK) { ef_destroy(c); return rc; }
+#define A(ptr, count) if ((rc = dev_alloc(c, &(ptr), (count))) != EF_OK) return rc;
     for (int b = 0; b < 2; b++) {
         A(c->d_es2[b], cfg->es_capacity + 1024);
         A(c->d_es_off2[b], (size_t)n + 1);
@@ -290,7 +293,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
 
     EfTables t;
     const int bad = ef_build_tables(&t);
-    if (bad) { ef_destroy(c); return fail(EF_EINVAL, "internal: VLC table %d does not fit its lookup shape", bad); }
+    if (bad) return fail(EF_EINVAL, "internal: VLC table %d does not fit its lookup shape", bad);
     CK(cudaMemcpy(dt, &t, sizeof(t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_default_intra, ef_default_intra_ptr(), 64, cudaMemcpyHostToDevice));
     for (int b = 0; b < 2; b++) {
@@ -298,12 +301,13 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
         CK(cudaMemset(c->d_es_off2[b], 0, ((size_t)n + 1) * 8));
     }
     CK(cudaMemset(c->d_overlay, 0, 1280));
-    { int rcp = push_dev(c); if (rcp != EF_OK) { ef_destroy(c); return rcp; } }
-    *out = c;
+    { int rcp = push_dev(c); if (rcp != EF_OK) return rcp; }
     rc = ef_reset(c);
-    if (rc != EF_OK) { ef_destroy(c); *out = nullptr; return rc; }
+    if (rc != EF_OK) return rc;
     rc = ef_video_init(c, 1);
-    if (rc != EF_OK) { ef_destroy(c); *out = nullptr; return rc; }
+    if (rc != EF_OK) return rc;
+    guard.c = nullptr;
+    *out = c;
     return EF_OK;
 }
 
@@ -756,11 +760,12 @@ int ef_blit(ef_ctx* c, int stream_index, int fb, uint16_t* dst, int line, int x,
 {
     DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c || !dst) return fail(EF_EINVAL, "null argument");
-    if (line < 0 || line >= EF_H || x < 0 || width < 0 || (x & ~3) + width > EF_W) return fail(EF_EINVAL, "blit span out of range");
+    const int w8 = (width + 7) & ~7;          // the reference loop advances 8 pixels per iteration (video.cpp:709): the whole last group is written
+    if (line < 0 || line >= EF_H || x < 0 || width < 0 || (x & ~3) + w8 > EF_W) return fail(EF_EINVAL, "blit span out of range (the width is rounded up to a multiple of 8 pixels)");
     int f; int rc = resolve_fb(c, stream_index, fb, &f);
     if (rc != EF_OK) return rc;
-    const int w8 = (width + 7) & ~7;          // the reference loop advances 8 pixels per iteration (video.cpp:709)
     if (!w8) return EF_OK;
+    CK(cudaDeviceSynchronize());              // like ef_read_frame: a decode may still be running on a non-blocking user stream
     rc = ensure_stage(c, EF_FRAME);
     if (rc != EF_OK) return rc;
     CK(ef_launch_blit(c->d, stream_index, f, line, x, w8, frame_counter, (uint16_t*)c->d_stage, 0));

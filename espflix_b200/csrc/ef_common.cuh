@@ -48,6 +48,9 @@
 #ifndef EF_K1A_LUT_BITS
 #define EF_K1A_LUT_BITS 10       // K1a: the two-symbol coefficient table is indexed by the next 2^K bits of the stream
 #endif
+#ifndef EF_K1B_PIN16
+#define EF_K1B_PIN16 1           // K1b: clamp two pixels per DPX instruction (VIADDMNMX.S16x2) instead of one
+#endif
 #ifndef EF_K1B_WARPS
 #define EF_K1B_WARPS 7       // K1b (reconstruct): warps per CTA, CTAs per SM
 #endif

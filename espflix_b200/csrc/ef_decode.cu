@@ -132,7 +132,7 @@ struct SliceState {
     BitReader br;
     uint32_t* wptr;          // coefficient list of the macroblock in flight (HBM); entries are stored at wptr[cnt]
     uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture | destination frame store << 31
-    const uint32_t* qz;      // scan-order quantiser | prescale | raster index tables [intra 64 | non-intra 64] in global memory: the defaults (EfTables::qz, L1 resident) or the stream's own
+    const uint32_t* qz;      // scan-order quantiser | prescale | raster index tables [intra 64 | non-intra 64] of a stream with its OWN matrices (global memory); nullptr = the defaults, served from shared memory
     int mbw, mbh;
     int mb_x, mb_y;          // last macroblock handled
     int first;               // next macroblock is the first of the slice (Q6)
@@ -195,15 +195,22 @@ __device__ __forceinline__ void idct8(int (&v)[8])
 
 __device__ __forceinline__ uint32_t pin4(uint32_t pred, int r0, int r1, int r2, int r3)
 {
-    // PIN(b + (s >> 8)) for four pixels (add_block, player.cpp:1189; _pin clamps to [0,248], Q1), with the
-    // residuals r still scaled by 256: t = max(min(pred * 256 + r, 248 * 256 + 255), 0) is one DPX instruction
-    // and floor(t / 256) = its byte 1 = clamp(pred + floor(r / 256)) exactly, for any 32-bit r in the IDCT's
-    // range. One PRMT puts a prediction byte into byte 1, three more gather the four result bytes.
+    // PIN(b + (s >> 8)) for four pixels (add_block, player.cpp:1189; _pin clamps to [0,248], Q1), with the residuals r
+    // still scaled by 256. Two pixels per DPX instruction: PRMT cuts (r >> 8) out of bytes 1-2 of two residuals as a pair
+    // of int16 (|r >> 8| < 30,500 for any coefficients within +-2048: the 64 basis amplitudes sum to 14.85), another PRMT
+    // spreads two prediction bytes to halfwords, VIADDMNMX.S16x2.RELU computes max(min(pred + res, 248), 0) on both.
+#if EF_K1B_PIN16
+    const uint32_t s01 = __viaddmin_s16x2_relu(__byte_perm(pred, 0, 0x4140), __byte_perm((uint32_t)r0, (uint32_t)r1, 0x6521), 0x00F800F8u);
+    const uint32_t s23 = __viaddmin_s16x2_relu(__byte_perm(pred, 0, 0x4342), __byte_perm((uint32_t)r2, (uint32_t)r3, 0x6521), 0x00F800F8u);
+    return __byte_perm(s01, s23, 0x6420);
+#else
+    // one pixel per instruction: t = max(min(pred * 256 + r, 248 * 256 + 255), 0), floor(t / 256) = its byte 1
     const int p0 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4404), r0, 0xF8FF);
     const int p1 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4414), r1, 0xF8FF);
     const int p2 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4424), r2, 0xF8FF);
     const int p3 = __viaddmin_s32_relu((int)__byte_perm(pred, 0, 0x4434), r3, 0xF8FF);
     return __byte_perm(__byte_perm(p0, p1, 0x0051), __byte_perm(p2, p3, 0x0051), 0x5410);
+#endif
 }
 
 // (a+b+1)>>1 on four packed bytes (mocomp cases 1 and 2, player.cpp:777-805)
@@ -464,7 +471,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
     const uint32_t n_slots = (uint32_t)D.n_streams * (EF_MBW_MAX * EF_MBH_MAX);
 
     SliceState s;
-    s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qz = D.tables->qz; s.mbw = 0; s.mb_x = s.mb_y = 0;
+    s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qz = nullptr; s.mbw = 0; s.mb_x = s.mb_y = 0;
     s.br.sring = smem_u32(smem + kTableBytes + kLutBytes) + threadIdx.x * 4;
     bool active = false, exhausted = false, busy = false;
     // the macroblock in flight: info word under construction (bit 0 set = a record is owed), entry count |
@@ -517,7 +524,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                         const EfSeq* seq = D.seq + (size_t)w.stream * (D.max_seq + 1) + (w.info >> 16);
                         s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
                         s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
-                        s.qz = seq->custom ? (const uint32_t*)seq->qz : (const uint32_t*)D.tables->qz;
+                        s.qz = seq->custom ? (const uint32_t*)seq->qz : nullptr;
                         const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
                         s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
                         s.slot_base |= ((D.base_pics[w.stream] + w.pic + 1u) & 1u) << 31;      // destination frame store: flush_picture(), player.cpp:692
@@ -551,8 +558,11 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
         // (one or two run/level codes with their sign bits, a closing '10') is taken in one step. Long codes,
         // the escape, invalid prefixes and symbols that would run past scan position 63 decode one symbol
         // through the clz-indexed table (and fold a following end of block in).
-        const uint32_t* qrow = s.qz + (intra ? 0 : 64);
+        const int qoff = intra ? 0 : 64;
         const int kq = intra ? 0 : 1;
+        // table word of scan position n: shared memory for the default matrices (no global-load latency in the symbol
+        // chain), the stream's own table in HBM otherwise (sequence headers that load matrices are rare)
+        auto qword = [&](int pos) -> uint32_t { return s.qz ? __ldg(s.qz + qoff + pos) : T.qz[qoff + pos]; };
         for (;;) {
             const unsigned bmask = __ballot_sync(0xFFFFFFFFu, busy);
             if (!bmask) break;
@@ -564,8 +574,8 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                 const uint32_t fl = st.fl;
                 const int len = st.len;
                 ctx = 0;
-                if (fl & EF_STEP_COEF1) { n += st.run1; s.wptr[cnt++] = ef_coef_entry(__ldg(qrow + n), st.lvl1, s.qscale, kq, blk24); n++; }
-                if (fl & EF_STEP_COEF2) { n += st.run2; s.wptr[cnt++] = ef_coef_entry(__ldg(qrow + n), st.lvl2, s.qscale, kq, blk24); n++; }
+                if (fl & EF_STEP_COEF1) { n += st.run1; s.wptr[cnt++] = ef_coef_entry(qword(n), st.lvl1, s.qscale, kq, blk24); n++; }
+                if (fl & EF_STEP_COEF2) { n += st.run2; s.wptr[cnt++] = ef_coef_entry(qword(n), st.lvl2, s.qscale, kq, blk24); n++; }
                 if (fl & 16u) {                                // give up on this and the remaining blocks, end the slice
                     info_acc |= (blkbit << 6) | ((uint32_t)cbp_rem << 14);
                     s.mb_y = s.mbh;

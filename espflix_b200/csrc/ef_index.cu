@@ -91,13 +91,27 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
         const uint64_t o = chunk + (uint64_t)lane * 16;
         load_chunk(chunk + 1024, v2, nxt2);
         const uint32_t w[5] = { v.x, v.y, v.z, v.w, nxt };
-        uint32_t hits = 0;
+        // "00 00 01" at byte i of the lane's 20-byte window, all 16 positions at once: exact per-byte masks of the zero
+        // bytes and of the bytes equal to 1 (0x80 in the byte), shifted against each other across the word boundaries
+        // (about 3 integer operations per stream byte; the per-position compare it replaces took 10 and made the scan
+        // ALU bound: profiles/r02_k0_ncu.txt). Positions before the stream or within 4 bytes of its end are dropped below.
+        uint32_t zm[5], om[5];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            // little-endian words: bytes i..i+3 of the 20-byte window
-            const uint32_t q = __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], (i & 3) * 8);
-            const int64_t at = (int64_t)(o + i) - (int64_t)misalign;          // stream-relative position of the first zero byte
-            if ((q & 0x00FFFFFFu) == 0x00010000u && at >= 0 && (uint64_t)at + 4 <= len) hits |= 1u << i;
+        for (int k = 0; k < 5; k++) {
+            const uint32_t x = w[k] ^ 0x01010101u;
+            zm[k] = ~(((w[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w[k]) & 0x80808080u;
+            om[k] = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+        }
+        uint32_t hits = 0;
+        uint32_t any = 0, hm[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            hm[k] = zm[k] & __funnelshift_r(zm[k], zm[k + 1], 8) & __funnelshift_r(om[k], om[k + 1], 16);
+            any |= hm[k];
+        }
+        if (any) {                                                            // bit 7 of byte j of word k -> bit 4k + j
+#pragma unroll
+            for (int k = 0; k < 4; k++) hits |= ((((hm[k] >> 7) * 0x00204081u) >> 21) & 15u) << (4 * k);
         }
         unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
         while (lanes && !stop) {
@@ -107,6 +121,7 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
             while (h && !stop) {
                 const int i = __ffs(h) - 1;
                 h &= h - 1;
+                if (obase + i < misalign || obase + i - misalign + 4 > len) continue;   // window bytes outside the stream (alignment slack, tail)
                 const uint64_t pos = obase + i - misalign;                    // first 00 of the start code
                 // the start-code value is byte i + 3 of the owning lane's 20-byte window: a shuffle, not another
                 // dependent global load per start code (the sweep is latency bound, ~170 start codes per stream)
@@ -129,7 +144,7 @@ ef_scan_kernel(EfDev* __restrict__ Dp)
                         pics[idx] = p;
                     }
                 } else if (code >= 0x01 && code <= 0xAF) {                    // slice start code
-                    if (n_pic > 0) {
+                    if (n_pic > 0 && n_pic <= (uint32_t)D.max_pictures) {     // slices of pictures beyond max_pictures are dropped with them (info[3] flags the overflow)
                         const uint32_t j = n_slice++;
                         if (j < (uint32_t)D.max_slices && lane == 0) { soff[j] = (uint32_t)(pos + 4); scode[j] = (uint8_t)code; }
                     }

@@ -4,6 +4,8 @@
 // pop_empty -> fill Buffer with <= 8 TS packets -> push_full, decoder thread in run(), frames
 // captured from push_video, final flush_picture(1). Usage: ef_player_cli in.ts out.i420 [field.u16 ntsc]
 //   or, with the offline PTS -> field pacing: ef_player_cli in.ts out.i420 --paced fields.u16 ntsc frame_counter0 max_fields
+//      (a 9th argument M = 2 | 3 presents the last picture as load_poster() does, flush_picture(M), and lets the poster
+//       scroll run for 17 more fields: espflix.cpp:1068, video.cpp:1041)
 //   or, with the audio of the program:        ef_player_cli in.ts out.i420 --audio out.pcm out.pdm
 // Prints {"frames": N, "seconds": S, "frames_per_s": R, ...}: the level-1 drop-in rate of one stream (run() to join).
 #include <stdio.h>
@@ -90,7 +92,8 @@ int main(int argc, char** argv)
     b->len = 0;
     dec.push_full(b);
     th.join();
-    dec.flush_picture(1);
+    const int last_mode = paced && argc >= 9 ? atoi(argv[8]) : 1;
+    dec.flush_picture(last_mode);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (audio) {
         const int nf = ef_audio_drain();
@@ -105,6 +108,8 @@ int main(int argc, char** argv)
         // the field in which the last frame flipped is completed by the line interrupt, as it would be on air
         std::vector<uint16_t> line(1136 + 64);
         while (_line_counter != 0) video_isr(line.data());
+        if (last_mode > 1)                         // the poster scroll: 17 more fields
+            for (int f = 0; f < 17; f++) do video_isr(line.data()); while (_line_counter != 0);
         FILE* ff = fopen(argv[4], "wb");
         fwrite(g_fields.data(), 2, g_fields.size(), ff);
         fclose(ff);

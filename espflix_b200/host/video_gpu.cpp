@@ -18,6 +18,7 @@ int16_t _hscroll = 0;
 uint8_t _video_composite[VIDEO_COMPOSITE_HEIGHT * VIDEO_COMPOSITE_WIDTH];
 int _video_composite_blend = 0;
 int _video_composite_progress = 0;
+int16_t _animate = 0, _animate_index = 0;  // poster scroll: push_video modes 2 / 3 (video.cpp:941-942, 1041)
 int8_t _next_frame = -1;                  // video.cpp:936
 uint32_t _next_frame_time = 0;
 uint32_t _video_pts = 0, _pts_origin = 0, _video_frame_counter_origin = 0;   // video.cpp:945-948
@@ -52,6 +53,15 @@ void upload(Frame* f, int fb = 0)
     if (ef_write_frame(g_ctx, 0, fb, g_staging.data()) != EF_OK) fprintf(stderr, "video: %s\n", ef_last_error());
 }
 }  // namespace
+
+// ease in / ease out of the poster scroll, one step per field and one at the flip (animate(), video.cpp:1076-1088)
+static void animate()
+{
+    static const int16_t easd[16] = { 0, 8, 16, 24, 48, 72, 104, 136, 176, 216, 248, 280, 304, 328, 336, 344 };   // _easd
+    if (_animate_index == 0) { _hscroll = 0; return; }
+    if (_animate_index < 0) _hscroll = (int16_t)-easd[-(++_animate_index)];
+    else _hscroll = easd[--_animate_index];
+}
 
 void ef_set_push_video_hook(ef_push_video_hook hook, void* user) { g_hook = hook; g_hook_user = user; }
 void ef_set_video_pacing(int on, ef_field_sink sink, void* user) { g_pacing = on != 0; g_sink = sink; g_sink_user = user; }
@@ -125,7 +135,7 @@ void push_video(Frame* f, int front, int64_t pts, int mode)   // video.cpp:1023
         _video_frame_counter_origin = (uint32_t)_frame_counter;
     }
     uint32_t d = (_video_pts - _pts_origin) + _video_frame_counter_origin;    // field counter value at which this frame is due
-    if (mode) d = (uint32_t)_frame_counter;        // any non-zero mode: due now
+    if (mode) { d = (uint32_t)_frame_counter; _animate = (int16_t)mode; }   // any non-zero mode: due now; 2 / 3 scroll the poster in
     if (d < (uint32_t)_frame_counter) {
         const int late = (int)((uint32_t)_frame_counter - d);
         printf("v late:%d\n", late);
@@ -154,7 +164,10 @@ extern "C" void video_isr(volatile void* vbuf)    // video.cpp:1122
         const bool active = i >= active_top && i < active_bottom && g_current != -1;
         if (!active && i < vsync_start && _next_frame != -1 && (uint32_t)_frame_counter >= _next_frame_time) {
             g_current = _next_frame;
+            if (_animate == 2) _animate_index = -16; else if (_animate == 3) _animate_index = 16;   // video.cpp:1168-1171
+            _animate = 0;
             _next_frame = -1;
+            animate();
             g_dirty = true;                        // the lines below this one show the new frame
         }
     }
@@ -181,6 +194,7 @@ extern "C" void video_isr(volatile void* vbuf)    // video.cpp:1122
         if (g_pacing && g_sink) g_sink(g_emitted.data(), g_line_width, g_line_count, (uint32_t)_frame_counter, g_sink_user);
         _line_counter = 0; _frame_counter = _frame_counter + 1;
         if (_video_composite_blend > 0) --_video_composite_blend;
+        animate();
     }
 }
 

@@ -153,7 +153,9 @@ int ef_video_set_overlay(ef_ctx* ctx, const uint8_t* bitmap80x16, int blend, int
 int ef_read_field(ef_ctx* ctx, int stream_index, uint16_t* dst /* line_count*line_width */);
 /* video_isr-style single line fetch from the last synthesised field of stream_index. */
 int ef_video_isr(ef_ctx* ctx, int stream_index, int line, uint16_t* buf /* line_width */);
-/* blit(): width luma pixels starting at x of line (0..191) -> 2*width samples at dst (host). */
+/* blit(): luma pixels x & ~3 .. of line (0..191) -> samples at dst (host). Like the reference loop (video.cpp:709) it
+ * works in groups of 8 pixels: 2 * round_up(width, 8) samples are written, starting at dst + 80 under PAL (blit() itself
+ * offsets its output there, video.cpp:698); (x & ~3) + round_up(width, 8) must not exceed 352. Synchronous. */
 int ef_blit(ef_ctx* ctx, int stream_index, int fb, uint16_t* dst, int line, int x, int width, int frame_counter);
 
 /* Pinned host memory for the asynchronous entry points (ef_submit_es_host, ef_read_latest_i420_async,

@@ -886,8 +886,10 @@ size_t efo_build_idx(const uint8_t* const ts[3], const size_t len[3], uint8_t* o
 /* ================================================================================================
  * PTS -> field pacing (video.cpp:1023-1057, 1122-1198), instant-decoder model.
  * ================================================================================================ */
-long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int ntsc, uint32_t frame_counter0, long max_fields,
-                        uint32_t* flip_field, int* flip_line)
+static const int16_t efo_easd[16] = { 0, 8, 16, 24, 48, 72, 104, 136, 176, 216, 248, 280, 304, 328, 336, 344 };   /* _easd, video.cpp:1077 */
+
+long efo_paced_schedule_ex(const int64_t* pts, const int* modes, int n_frames, int ntsc, uint32_t frame_counter0, long max_fields, long tail_fields,
+                           uint32_t* flip_field, int* flip_line, int16_t* field_hscroll)
 {
     const int line_count = ntsc ? 262 : 312;
     const int active_top = 32 + (ntsc ? 0 : 32), active_bottom = active_top + 192;      /* video.cpp:1135-1137 */
@@ -895,7 +897,8 @@ long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int 
     uint32_t frame_counter = frame_counter0;
     uint32_t video_pts, pts_origin = 0, fc_origin = 0, next_time = 0;
     int current = -1, next = -1, k = 0;
-    long fields = 0;
+    int animate = 0, animate_index = 0, hscroll = 0;                  /* _animate, _animate_index, _hscroll (video.cpp:939-942) */
+    long fields = 0, tail = -1;
     while (fields < max_fields) {
         for (int i = 0; i < line_count; i++) {
             if (next == -1 && k < n_frames) {                         /* push_video(k), video.cpp:1023 */
@@ -903,17 +906,22 @@ long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int 
                 video_pts = (uint32_t)p;
                 if (fc_origin == 0) { pts_origin = video_pts; fc_origin = frame_counter; }
                 uint32_t d = (video_pts - pts_origin) + fc_origin;
-                if (modes && modes[k]) d = frame_counter;           /* non-zero mode: due now, video.cpp:1039 */
+                if (modes && modes[k]) { d = frame_counter; animate = modes[k]; }   /* non-zero mode: due now; 2 / 3 start the poster scroll, video.cpp:1039-1042 */
                 if (d < frame_counter) {
                     const int late = (int)(frame_counter - d);
                     if (late > 2) fc_origin = 0;                       /* more than two fields late: re-latch the origin at the next push */
                 }
                 next_time = d; next = k & 1;
             }
+            if (i == active_top && field_hscroll) field_hscroll[fields] = (int16_t)hscroll;
             const int active = i >= active_top && i < active_bottom && current != -1;
             if (!active && i < vsync_start) {                          /* the else branch of video_isr: flip buffers in blanking */
                 if (next != -1 && frame_counter >= next_time) {
                     current = next; next = -1;
+                    if (animate == 2) animate_index = -16; else if (animate == 3) animate_index = 16;     /* video.cpp:1168-1171 */
+                    animate = 0;
+                    /* animate(), video.cpp:1078-1088 */
+                    if (animate_index == 0) hscroll = 0; else if (animate_index < 0) hscroll = -efo_easd[-(++animate_index)]; else hscroll = efo_easd[--animate_index];
                     flip_field[k] = frame_counter; flip_line[k] = i;
                     k++;
                 }
@@ -921,7 +929,17 @@ long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int 
         }
         frame_counter++;
         fields++;
-        if (k >= n_frames && next == -1) break;
+        if (animate_index == 0) hscroll = 0; else if (animate_index < 0) hscroll = -efo_easd[-(++animate_index)]; else hscroll = efo_easd[--animate_index];   /* animate() at the end of every field, video.cpp:1195 */
+        if (k >= n_frames && next == -1) {
+            if (tail < 0) tail = tail_fields;
+            if (tail-- <= 0) break;
+        }
     }
     return fields;
+}
+
+long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int ntsc, uint32_t frame_counter0, long max_fields,
+                        uint32_t* flip_field, int* flip_line)
+{
+    return efo_paced_schedule_ex(pts, modes, n_frames, ntsc, frame_counter0, max_fields, 0, flip_field, flip_line, NULL);
 }

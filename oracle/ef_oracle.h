@@ -85,9 +85,13 @@ void efo_field_ex(const efo_video* v, const uint8_t* strips_a, const uint8_t* st
  * interrupt only advances while a frame is queued. flip_field[k] / flip_line[k] = _frame_counter and line at
  * which frame k becomes _current_frame. Returns the number of whole fields emitted up to and including the one
  * in which the last frame flipped (stops at max_fields). modes (may be NULL = all 0): 1 = show at once, as
- * MpegDecoder::flush_picture(1) pushes the last picture; 2/3 (poster scroll animation) are not modelled. */
+ * MpegDecoder::flush_picture(1) pushes the last picture; 2 / 3 also start the poster scroll animation (_animate, animate(),
+ * _easd: video.cpp:1041, 1076-1088, 1168-1174): the _ex form reports the _hscroll each field's active lines are drawn with
+ * (field_hscroll[field], may be NULL) and keeps the line interrupt running for tail_fields more fields after the last flip. */
 long efo_paced_schedule(const int64_t* pts, const int* modes, int n_frames, int ntsc, uint32_t frame_counter0, long max_fields,
                         uint32_t* flip_field, int* flip_line);
+long efo_paced_schedule_ex(const int64_t* pts, const int* modes, int n_frames, int ntsc, uint32_t frame_counter0, long max_fields, long tail_fields,
+                           uint32_t* flip_field, int* flip_line, int16_t* field_hscroll);
 
 /* ---- trick-mode index (indexer/indexer.cpp:90-253) --------------------------------------
  * make_index(): table of (PES pts, TS packet number) of every video packet that starts a PES whose payload

@@ -35,6 +35,7 @@ extern uint32_t _next_frame_time;
 void video_reset();
 void push_video(Frame* f, int front, int64_t pts, int mode);   // video.cpp:1023
 extern int16_t _hscroll;
+extern int16_t _animate, _animate_index;                        // poster scroll state (video.cpp:941-942)
 extern Frame* _frames;
 extern uint32_t _color_tab[256 * 3];
 extern int16_t* _burst0;
@@ -140,12 +141,23 @@ void efref_blit(const uint8_t* i420, int frame_counter, uint16_t* dst, int line,
 // time passes only while the decoder waits for presentation. Deterministic, and the only model an offline
 // throughput build can have. Returns the number of whole fields emitted (<= max_fields); flip_field/flip_line[k]
 // = _frame_counter and line at which frame k became _current_frame. `out` (may be NULL) receives the fields.
+long efref_paced_ex(const uint8_t* i420_frames, int n_frames, const int64_t* pts, const int* modes, int frame_counter0, int max_fields, int tail_fields,
+                    uint16_t* out, uint32_t* flip_field, int* flip_line, int16_t* field_hscroll);
 long efref_paced(const uint8_t* i420_frames, int n_frames, const int64_t* pts, const int* modes, int frame_counter0, int max_fields,
                  uint16_t* out, uint32_t* flip_field, int* flip_line)
+{
+    return efref_paced_ex(i420_frames, n_frames, pts, modes, frame_counter0, max_fields, 0, out, flip_field, flip_line, nullptr);
+}
+
+// the same with `tail_fields` more fields after the last flip (the poster scroll of push_video modes 2 / 3 runs for 16 fields,
+// video.cpp:1076-1088) and, optionally, the _hscroll the active lines of every field were drawn with
+long efref_paced_ex(const uint8_t* i420_frames, int n_frames, const int64_t* pts, const int* modes, int frame_counter0, int max_fields, int tail_fields,
+                    uint16_t* out, uint32_t* flip_field, int* flip_line, int16_t* field_hscroll)
 {
     video_reset();
     _frames = g_fb; _current_frame = -1; _next_frame = -1; _next_frame_time = 0;
     _line_counter = 0; _frame_counter = frame_counter0; _hscroll = 0; _video_composite_blend = 0;
+    _animate = 0; _animate_index = 0;                               // a previous run may have stopped in the middle of a scroll
     std::atomic<int> done(0), pushed(0);
     std::thread decoder([&] {
         for (int k = 0; k < n_frames; k++) {
@@ -160,10 +172,12 @@ long efref_paced(const uint8_t* i420_frames, int n_frames, const int64_t* pts, c
     lb[1] = (uint16_t*)calloc(_line_width + 64, 2);
     const int lines = _line_count, w = _line_width;
     long fields = 0;
-    int flips = 0;
+    int flips = 0, tail = -1;
     bool stuck = false;
+    const int active_top = 32 + (g_std ? 0 : 32);
     while (fields < max_fields && !stuck) {
         for (int l = 0; l < lines && !stuck; l++) {
+            if (l == active_top && field_hscroll) field_hscroll[fields] = _hscroll;
             const auto t0 = std::chrono::steady_clock::now();
             while (_next_frame == -1 && !done) {                            // wait for the decoder to queue its next frame
                 std::this_thread::yield();
@@ -177,7 +191,10 @@ long efref_paced(const uint8_t* i420_frames, int n_frames, const int64_t* pts, c
             if (out) memcpy(out + ((size_t)fields * lines + l) * w, lb[l & 1], (size_t)w * 2);
         }
         fields++;
-        if (done && _next_frame == -1) break;                               // last frame is on screen for this whole field
+        if (done && _next_frame == -1) {                                    // last frame is on screen for this whole field
+            if (tail < 0) tail = tail_fields;
+            if (tail-- <= 0) break;
+        }
     }
     if (!done) {                                                            // stopped early: never leave the decoder thread parked
         _frame_counter = 0x7FFFFFF0;

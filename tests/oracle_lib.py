@@ -50,6 +50,8 @@ class Oracle:
         L.efo_stats_get.argtypes = [VP]
         L.efo_paced_schedule.restype = ctypes.c_long
         L.efo_paced_schedule.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_long, VP, VP]
+        L.efo_paced_schedule_ex.restype = ctypes.c_long
+        L.efo_paced_schedule_ex.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_long, ctypes.c_long, VP, VP, VP]
         L.efo_make_index.restype = ctypes.c_int
         L.efo_make_index.argtypes = [VP, ctypes.c_size_t, VP, VP, ctypes.c_int, VP, VP]
         L.efo_pts2seq.restype = ctypes.c_int
@@ -135,9 +137,9 @@ class Oracle:
         self.lib.efo_field(ctypes.byref(v), strips.ctypes.data, frame_counter, out.ctypes.data)
         return out
 
-    def paced(self, frames, pts, ntsc, frame_counter0, max_fields, want_fields=True, modes=None):
+    def paced(self, frames, pts, ntsc, frame_counter0, max_fields, want_fields=True, modes=None, tail_fields=0, want_hscroll=False):
         """push_video + video_isr of the unmodified reference under the instant-decoder model.
-        Returns (fields, flip_field[], flip_line[], field stream or None)."""
+        Returns (fields, flip_field[], flip_line[], field stream or None[, hscroll per field])."""
         g = self.init(ntsc)
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         pts = np.ascontiguousarray(pts, dtype=np.int64)
@@ -145,10 +147,12 @@ class Oracle:
         ff, fl = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.int32)
         out = np.zeros(max_fields * g[0] * g[1], dtype=np.uint16) if want_fields else None
         md = None if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
-        r = self.lib.efref_paced(frames.ctypes.data, n, pts.ctypes.data, None if md is None else md.ctypes.data, frame_counter0, max_fields,
-                                 out.ctypes.data if want_fields else None, ff.ctypes.data, fl.ctypes.data)
+        hs = np.zeros(max_fields + 1, dtype=np.int16)
+        r = self.lib.efref_paced_ex(frames.ctypes.data, n, pts.ctypes.data, None if md is None else md.ctypes.data, frame_counter0, max_fields, tail_fields,
+                                    out.ctypes.data if want_fields else None, ff.ctypes.data, fl.ctypes.data, hs.ctypes.data)
         assert r >= 0, "reference pacing harness timed out"
-        return int(r), ff, fl, (out[:r * g[0] * g[1]] if want_fields else None)
+        res = (int(r), ff, fl, (out[:r * g[0] * g[1]] if want_fields else None))
+        return res + (hs[:r].copy(),) if want_hscroll else res
 
     def field_ex(self, i420_a, i420_b, ntsc, frame_counter, hscroll=0, bitmap=None, blend=0, progress=0):
         v = self.video(ntsc)
@@ -174,14 +178,15 @@ class Oracle:
         self.lib.efo_stats_get(ctypes.byref(s))
         return s
 
-    def paced_schedule(self, pts, ntsc, frame_counter0, max_fields=1 << 20, modes=None):
-        """push_video pacing, instant-decoder model: (fields, flip_field[], flip_line[])"""
+    def paced_schedule(self, pts, ntsc, frame_counter0, max_fields=1 << 20, modes=None, tail_fields=0, want_hscroll=False):
+        """push_video pacing, instant-decoder model: (fields, flip_field[], flip_line[][, hscroll per field])"""
         pts = np.ascontiguousarray(pts, dtype=np.int64)
         ff, fl = np.zeros(len(pts), dtype=np.uint32), np.zeros(len(pts), dtype=np.int32)
         md = None if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
-        n = self.lib.efo_paced_schedule(pts.ctypes.data, None if md is None else md.ctypes.data, len(pts), 1 if ntsc else 0, frame_counter0,
-                                        max_fields, ff.ctypes.data, fl.ctypes.data)
-        return int(n), ff, fl
+        hs = np.zeros(min(max_fields, 1 << 16) + 1, dtype=np.int16)
+        n = self.lib.efo_paced_schedule_ex(pts.ctypes.data, None if md is None else md.ctypes.data, len(pts), 1 if ntsc else 0, frame_counter0,
+                                           min(max_fields, 1 << 16), tail_fields, ff.ctypes.data, fl.ctypes.data, hs.ctypes.data)
+        return (int(n), ff, fl, hs[:n].copy()) if want_hscroll else (int(n), ff, fl)
 
     # -- trick-mode index (indexer/indexer.cpp) ----------------------------------------------------------
     def make_index(self, ts):
@@ -240,6 +245,8 @@ class RefVideo:
         self.lib.efref_field_ex.argtypes = [VP, VP, ctypes.c_int, ctypes.c_int, VP, ctypes.c_int, ctypes.c_int, VP]
         self.lib.efref_paced.restype = ctypes.c_long
         self.lib.efref_paced.argtypes = [VP, ctypes.c_int, VP, VP, ctypes.c_int, ctypes.c_int, VP, VP, VP]
+        self.lib.efref_paced_ex.restype = ctypes.c_long
+        self.lib.efref_paced_ex.argtypes = [VP, ctypes.c_int, VP, VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, VP, VP, VP, VP]
         self.std = None
 
     def init(self, ntsc):
@@ -257,9 +264,9 @@ class RefVideo:
         self.lib.efref_field(i420.ctypes.data, None, frame_counter, 0, out.ctypes.data)
         return out
 
-    def paced(self, frames, pts, ntsc, frame_counter0, max_fields, want_fields=True, modes=None):
+    def paced(self, frames, pts, ntsc, frame_counter0, max_fields, want_fields=True, modes=None, tail_fields=0, want_hscroll=False):
         """push_video + video_isr of the unmodified reference under the instant-decoder model.
-        Returns (fields, flip_field[], flip_line[], field stream or None)."""
+        Returns (fields, flip_field[], flip_line[], field stream or None[, hscroll per field])."""
         g = self.init(ntsc)
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         pts = np.ascontiguousarray(pts, dtype=np.int64)
@@ -267,10 +274,12 @@ class RefVideo:
         ff, fl = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.int32)
         out = np.zeros(max_fields * g[0] * g[1], dtype=np.uint16) if want_fields else None
         md = None if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
-        r = self.lib.efref_paced(frames.ctypes.data, n, pts.ctypes.data, None if md is None else md.ctypes.data, frame_counter0, max_fields,
-                                 out.ctypes.data if want_fields else None, ff.ctypes.data, fl.ctypes.data)
+        hs = np.zeros(max_fields + 1, dtype=np.int16)
+        r = self.lib.efref_paced_ex(frames.ctypes.data, n, pts.ctypes.data, None if md is None else md.ctypes.data, frame_counter0, max_fields, tail_fields,
+                                    out.ctypes.data if want_fields else None, ff.ctypes.data, fl.ctypes.data, hs.ctypes.data)
         assert r >= 0, "reference pacing harness timed out"
-        return int(r), ff, fl, (out[:r * g[0] * g[1]] if want_fields else None)
+        res = (int(r), ff, fl, (out[:r * g[0] * g[1]] if want_fields else None))
+        return res + (hs[:r].copy(),) if want_hscroll else res
 
     def field_ex(self, i420_a, i420_b, ntsc, frame_counter, hscroll=0, bitmap=None, blend=0, progress=0):
         g = self.init(ntsc)

@@ -64,8 +64,11 @@ def test_video_isr_line_fetch_and_blit(ctx, oracle):
         w, n = ctx.geometry()
         for line in (0, 31, 32, 100, 223, 224, n - 1):
             assert np.array_equal(ctx.video_isr(2, line), want[line * w:(line + 1) * w]), line
-        for line, x, width in ((0, 0, 352), (191, 0, 352), (77, 16, 64), (100, 8, 344)):
+        for line, x, width in ((0, 0, 352), (191, 0, 352), (77, 16, 64), (100, 8, 344), (50, 4, 20), (9, 330, 3)):
             assert np.array_equal(ctx.blit(2, 0, line, x, width, 1), oracle.blit(fr, ntsc, line, x, width, 1)), (ntsc, line, x, width)
+        import espflix_b200
+        with pytest.raises(espflix_b200.EspflixError):      # the last 8-pixel group would run past the line (width is rounded up to 8)
+            ctx.blit(2, 0, 10, 348, 4, 1)
 
 
 def test_decode_then_composite_latest_frame(oracle):

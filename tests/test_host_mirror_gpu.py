@@ -59,7 +59,7 @@ def test_mirrored_index_builder_on_reference_fixture(tmp_path):
     assert got == open(os.path.join(G, "video_idx_fixture.bin"), "rb").read()
 
 
-@pytest.mark.parametrize("name", ["ntsc_fc1", "pal_fc5", "ntsc_fc0_quirk"])
+@pytest.mark.parametrize("name", ["ntsc_fc1", "pal_fc5", "ntsc_fc0_quirk", "ntsc_poster3", "pal_poster2"])
 def test_mirrored_presentation_pacing(name, tmp_path):
     """push_video with the offline PTS -> field pacing (ef_set_video_pacing): the decoder mirror pushes its
     frames, push_video drives video_isr until each frame has flipped, and the stream of fields that reaches the
@@ -70,8 +70,8 @@ def test_mirrored_presentation_pacing(name, tmp_path):
     ts_path = os.path.join(str(tmp_path), "in.ts")
     open(ts_path, "wb").write(synth.wrap_ts(es, off).tobytes())
     out, fields = os.path.join(str(tmp_path), "out.i420"), os.path.join(str(tmp_path), "fields.u16")
-    r = subprocess.run([ef_build.HOST_CLI, ts_path, out, "--paced", fields, str(p["ntsc"]), str(p["frame_counter0"]), str(p["max_fields"])],
-                       capture_output=True, timeout=600, check=True)
+    r = subprocess.run([ef_build.HOST_CLI, ts_path, out, "--paced", fields, str(p["ntsc"]), str(p["frame_counter0"]), str(p["max_fields"]), str(p["modes"][-1])],
+                       capture_output=True, timeout=600, check=True)       # the last argument: flush_picture(mode); 2 / 3 = a poster scrolling in (load_poster)
     info = json.loads(r.stdout.decode().strip().splitlines()[-1])
     assert info["frames"] == p["pictures"] and info["fields"] == p["fields"]
     stream = np.fromfile(fields, dtype=np.uint16)

@@ -33,10 +33,14 @@ def _blocks(n, seed, dense):
     return (v * pre[None, :]).astype(np.int32)
 
 
-@pytest.mark.parametrize("dense", [False, True], ids=["sparse", "dense"])
-def test_tensor_core_idct_is_within_one_lsb(oracle, dense):
-    n = 128 * 148 * 4
-    coefs = _blocks(n, 11 + dense, dense)
+@pytest.mark.parametrize("dense,tiles_per_sm", [(False, 4), (True, 4), (False, 64)], ids=["sparse", "dense", "sparse_1.2M_blocks"])
+def test_tensor_core_idct_is_within_one_lsb(oracle, dense, tiles_per_sm):
+    n = 128 * 148 * tiles_per_sm                          # 64 tiles per SM = 1.2 M blocks: a throughput-sized run (one K1b launch rebuilds ~5.9 M)
+    if tiles_per_sm > 4:
+        small = _blocks(128 * 148 * 4, 13, dense)
+        coefs = np.ascontiguousarray(np.tile(small, (tiles_per_sm // 4, 1)))
+    else:
+        coefs = _blocks(n, 11 + dense, dense)
     L = idct_linear.matrix()
     out, prep_ms, mma_ms = capi.idct_tc_run(coefs, L, repeats=5)
     want = coefs.copy()
@@ -55,5 +59,5 @@ def test_tensor_core_idct_is_within_one_lsb(oracle, dense):
            "blocks_per_s_mma": n / (mma_ms / 1000.0), "blocks_per_s_total": n / ((mma_ms + prep_ms) / 1000.0)}
     print("tcgen05 IDCT experiment:", json.dumps(rec))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "idct_tc_%s.json" % ("dense" if dense else "sparse")), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "idct_tc_%s%s.json" % ("dense" if dense else "sparse", "_large" if tiles_per_sm > 4 else "")), "w") as f:
         json.dump(rec, f)

@@ -17,8 +17,9 @@ PINS = json.load(open(os.path.join(ROOT, "tests", "golden", "pacing_pins.json"))
 def test_schedule_matches_reference_pins(name):
     p = PINS[name]
     pts = 129003 + 3003 * np.arange(p["pictures"], dtype=np.int64)
-    fields, ff, fl = Oracle().paced_schedule(pts, p["ntsc"], p["frame_counter0"], p["max_fields"], modes=p["modes"])
+    fields, ff, fl, hs = Oracle().paced_schedule(pts, p["ntsc"], p["frame_counter0"], p["max_fields"], modes=p["modes"], tail_fields=p["tail_fields"], want_hscroll=True)
     assert fields == p["fields"] and ff.tolist() == p["flip_field"] and fl.tolist() == p["flip_line"]
+    assert hs.tolist() == p["hscroll"]                    # the poster scroll (_animate / _easd) field by field
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
@@ -35,7 +36,9 @@ def test_schedule_matches_reference_on_irregular_pts():
         pts = np.maximum(pts, 0)
         fc0 = int(rng.integers(0, 4)) if case < 8 else int(rng.integers(1, 100000))
         fr = np.ascontiguousarray(np.broadcast_to(frames[0], (n, 101376)))
-        modes = (rng.random(n) < 0.15).astype(np.int32)
-        rf, rff, rfl, _ = rv.paced(fr, pts, ntsc, fc0, 400, want_fields=False, modes=modes)
-        f, ff, fl = o.paced_schedule(pts, ntsc, fc0, 400, modes=modes)
+        modes = np.where(rng.random(n) < 0.2, rng.integers(1, 4, size=n), 0).astype(np.int32)      # 1 at once, 2 / 3 poster scroll
+        tail = int(rng.integers(0, 20))
+        rf, rff, rfl, _, rhs = rv.paced(fr, pts, ntsc, fc0, 400, want_fields=False, modes=modes, tail_fields=tail, want_hscroll=True)
+        f, ff, fl, hs = o.paced_schedule(pts, ntsc, fc0, 400, modes=modes, tail_fields=tail, want_hscroll=True)
         assert (f, ff.tolist(), fl.tolist()) == (rf, rff.tolist(), rfl.tolist()), (case, ntsc, fc0, pts.tolist())
+        assert hs.tolist() == rhs.tolist(), (case, modes.tolist())
