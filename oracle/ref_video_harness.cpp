@@ -13,6 +13,8 @@
 #include <atomic>
 #include <chrono>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
 
 #include "player.h"   // reference headers: Frame, video_init, ...
 #undef printf
@@ -37,6 +39,8 @@ void push_video(Frame* f, int front, int64_t pts, int mode);   // video.cpp:1023
 extern int16_t _hscroll;
 extern int16_t _animate, _animate_index;                        // poster scroll state (video.cpp:941-942)
 extern Frame* _frames;
+extern std::mutex _event_guard;                                    // streamer.cpp:302-303 (desktop event group)
+extern std::condition_variable _event_signal;
 extern uint32_t _color_tab[256 * 3];
 extern int16_t* _burst0;
 extern int16_t* _burst1;
@@ -180,6 +184,11 @@ long efref_paced_ex(const uint8_t* i420_frames, int n_frames, const int64_t* pts
             if (l == active_top && field_hscroll) field_hscroll[fields] = _hscroll;
             const auto t0 = std::chrono::steady_clock::now();
             while (_next_frame == -1 && !done) {                            // wait for the decoder to queue its next frame
+                // the reference's desktop set_events() notifies without holding _event_guard (streamer.cpp:335-343), so a
+                // wake-up can fall between push_video's predicate check and its wait(): nudge the condition variable
+                // (state untouched) under the lock so a parked decoder always re-reads _event_group
+                { std::lock_guard<std::mutex> g(_event_guard); }
+                _event_signal.notify_all();
                 std::this_thread::yield();
                 if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) { stuck = true; break; }
             }
