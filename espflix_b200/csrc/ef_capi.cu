@@ -38,8 +38,8 @@ __global__ void ef_audio_ts_packet_kernel(const uint8_t* ts, uint64_t n_packets,
 __global__ void ef_audio_ts_scan_kernel(const uint64_t* pkt_off, int n_files, const uint8_t* start, const uint8_t* kind, uint32_t* out_pos, uint64_t* es_len);
 __global__ void ef_audio_ts_copy_kernel(const uint8_t* ts, const uint64_t* pkt_off, int n_files, uint64_t n_packets, const uint8_t* start, const uint32_t* out_pos, const uint64_t* es_off, uint8_t* es);
 cudaError_t ef_audio_upload_constants();
-cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, size_t max_slices, cudaStream_t stream);
-cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, size_t n_slots, cudaStream_t stream);
+cudaError_t ef_launch_parse(const EfDev& dev, int pic0, int n_pics, int sm_count, size_t max_slices, cudaStream_t stream);
+cudaError_t ef_launch_recon(const EfDev& dev, int pic_rel, int sm_count, size_t n_slots, cudaStream_t stream);
 cudaError_t ef_launch_composite(const EfDev* dev, int n_streams, const EfGeometry& g, int fb, int frame_counter, const EfPresent& pr, cudaStream_t stream);
 cudaError_t ef_launch_blit(const EfDev* dev, int stream_index, int fb, int line, int x, int width, int frame_counter, uint16_t* dst, cudaStream_t stream);
 
@@ -496,11 +496,13 @@ static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st, uint8_t* host
     CK(cudaMemsetAsync(c->h.mb_info, 0, slots * 4, st));
     CK(cudaMemsetAsync(c->h.parse_cursor, 0, ((size_t)k + 1) * 4, st));
     if (c->profiling) { CK(cudaEventRecord(c->ev_prof[2], st)); c->prof_decode = true; }
-    CK(ef_launch_parse(c->d, p0, k, c->sm_count, (size_t)k * c->cfg.n_streams * c->cfg.max_slices_per_picture, st));
+    EfDev dev = c->h;                                       // K1 takes the context by value (kernel parameter space)
+    dev.es = c->d_es2[c->active]; dev.es_off = c->d_es_off2[c->active];
+    CK(ef_launch_parse(dev, p0, k, c->sm_count, (size_t)k * c->cfg.n_streams * c->cfg.max_slices_per_picture, st));
     if (c->profiling) CK(cudaEventRecord(c->ev_prof[3], st));
     const size_t batch_bytes = (size_t)c->cfg.n_streams * EF_FRAME;
     for (int i = 0; i < k; i++) {
-        CK(ef_launch_recon(c->d, i, c->sm_count, (size_t)c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX, st));
+        CK(ef_launch_recon(dev, i, c->sm_count, (size_t)c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX, st));
         if (host_dst) {
             const int b = c->stage_idx ^= 1;
             int rc = ensure_stage2(c, b, batch_bytes);

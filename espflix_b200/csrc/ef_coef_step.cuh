@@ -88,3 +88,60 @@ static __host__ __device__ __forceinline__ uint32_t ef_coef_entry(uint32_t z, in
     const int v = neg ? -m : m;
     return (uint32_t)(v * EF_BYTE1(z) + (int)((z & 0x00FC0000u) | blk24));
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1a v3 (EF_K1A_V3): one symbol per step through the clz-indexed table, a following '10' folded in, and NO
+// arithmetic on the level: the parser stores a raw token and K1b dequantises while it expands the list (the same
+// instructions run there for 32 entries at once instead of for the ~14 lanes of a parser warp that are in a
+// coefficient at the same time).
+//   token = block << 27 | scan position << 21 | quantiser_scale << 16 | (int16) level
+// ---------------------------------------------------------------------------------------------------------------
+#define EF_SYM_COEF 0u
+#define EF_SYM_EOB 1u         // '10' on its own (an intra block without AC coefficients)
+#define EF_SYM_DERAIL 2u      // not a code: nothing consumed
+
+struct EfSym {
+    uint32_t kind;
+    int len, run, lvl;        // bits consumed (sign / escape payload included), zero run, signed level
+};
+
+static __host__ __device__ __forceinline__ EfSym ef_coef_sym(uint32_t w, bool first, const uint16_t* __restrict__ dct)
+{
+    EfSym r;
+    const int lz = EF_CLZ(w);
+    // row (context, leading zeros), column = the five bits after the leading one; row 12 is all-invalid (>= 12 zeros)
+    const int idx = w >= 0x00100000u ? (first ? 13 * 32 - 32 : -32) + lz * 32 + (int)((w << (lz & 31)) >> 26) : 12 * 32;
+    const uint32_t t = dct[idx];
+    r.len = (int)(t & 31u); r.run = (int)((t >> 5) & 31u);
+    const int mag = (int)(t >> 10);
+    r.kind = EF_SYM_COEF;
+    r.lvl = ((w >> ((32 - r.len) & 31)) & 1u) ? -mag : mag;          // sign = last bit of a regular code
+    if (mag == 0) {
+        if (r.len == 2) r.kind = EF_SYM_EOB;                          // player.cpp:1075
+        else if (r.len == 6) {                                        // escape: 6-bit run, 8- or 16-bit level (player.cpp:1092)
+            r.run = (int)((w >> 20) & 63u);
+            const int b = (int)((w >> 12) & 255u);
+            r.lvl = (int)(int8_t)b; r.len = 20;
+            if ((b & 127) == 0) { r.lvl = (int)((w >> 4) & 255u) - 2 * b; r.len = 28; }      // b = 0: 0..255, b = 128: -256..-1
+        } else r.kind = EF_SYM_DERAIL;
+    }
+    return r;
+}
+
+static __host__ __device__ __forceinline__ uint32_t ef_token(uint32_t blk, int n, int qscale, int level)
+{
+    return (blk << 27) | ((uint32_t)n << 21) | ((uint32_t)qscale << 16) | ((uint32_t)level & 0xFFFFu);
+}
+
+// block(), player.cpp:1106-1121, for one token: the dequantised, AAN-prescaled coefficient b[zz]. Same arithmetic as
+// ef_coef_entry above; z = table word of the scan position (quantiser | prescale << 8 | zz << 18), k = 1 when not intra.
+static __host__ __device__ __forceinline__ int ef_dequant(uint32_t z, int level, int qscale, int k)
+{
+    const int mag = level < 0 ? -level : level;
+    int neg = level < 0;
+    int m = ((2 * mag + k) * (qscale * (int)(z & 255u))) >> 4;
+    if (m == 0) neg = 0;
+    m = ((m > 1 ? m : 1) - 1) | 1;
+    m = m < 2047 + neg ? m : 2047 + neg;
+    return (neg ? -m : m) * EF_BYTE1(z);
+}

@@ -45,9 +45,32 @@
 #ifndef EF_K1A_HDR_BATCH
 #define EF_K1A_HDR_BATCH 32      // waiting lanes that end a symbol loop early; 32 = the loop runs until no lane is busy
 #endif
-#ifndef EF_K1A_LUT_BITS
-#define EF_K1A_LUT_BITS 10       // K1a: the two-symbol coefficient table is indexed by the next 2^K bits of the stream
+#ifndef EF_K1A_V3
+#define EF_K1A_V3 1              // K1a: one symbol per step through the clz-indexed table, a following end of block folded in (0: the two-symbol table step)
 #endif
+#ifndef EF_K1B_DEQUANT
+#define EF_K1B_DEQUANT 0         // 1: K1a v3 stores raw tokens and K1b dequantises while it expands the list (measured: K1a -4 %, K1b +12 %: lost)
+#endif
+#ifndef EF_K1A_ES16
+#define EF_K1A_ES16 1            // K1a: the bitstream comes in through 16-byte cp.async.cg chunks (4 per lane in flight) instead of 4-byte words: a quarter of the
+#endif                           //      scattered-address global-memory instructions, and no reliance on L1 hits
+#ifndef EF_K1A_STAGE
+#define EF_K1A_STAGE 32          // K1a: the first N list entries of a macroblock are staged in shared memory and written out by the whole warp, coalesced, when the
+#endif                           //      macroblock is complete (0: every entry is its own scattered 4-byte store)
+#ifndef EF_PROBE_NOSTORE
+#define EF_PROBE_NOSTORE 0       // measurement probe only: K1a drops its coefficient stores (output wrong)
+#endif
+#ifndef EF_K1A_RING_AHEAD
+#define EF_K1A_RING_AHEAD 1      // K1a: the word after `lo` is already in a register when a refill needs it (its ring load was issued one refill earlier)
+#endif
+#ifndef EF_K1A_LUT_BITS
+#if EF_K1A_V3
+#define EF_K1A_LUT_BITS 0
+#else
+#define EF_K1A_LUT_BITS 10
+#endif
+#endif
+// EF_K1A_LUT_BITS (EF_K1A_V3 = 0 only): the two-symbol coefficient table is indexed by the next 2^K bits of the stream
 #ifndef EF_K1B_PIN16
 #define EF_K1B_PIN16 1           // K1b: clamp two pixels per DPX instruction (VIADDMNMX.S16x2) instead of one
 #endif

@@ -51,6 +51,7 @@ constexpr int kDenseWords = 6 * kDenseStride;   // int32 [6][72] prescaled coeff
 constexpr int kDenseBytes = kDenseWords * 4;
 constexpr int kStageBytes = 4 * EF_TILE;        // motion-compensation staging: up to 2 x 2 reference tiles per macroblock
 constexpr int kWarpBytes = 2 * (kDenseBytes + kStageBytes) + 16;   // two macroblocks per warp + their mbarriers
+constexpr int kReconQzBytes = EF_K1B_DEQUANT ? 128 * 4 : 0;             // K1b dequantises (v3): the default matrices' table words, once per CTA
 
 struct SharedTables {                           // same layout as the head of EfTables
     uint16_t dct[26 * 32];
@@ -76,16 +77,61 @@ constexpr int kLutBytes = kLutBits > 0 ? 2 * kLutSize * (int)sizeof(uint2) : 0;
 // the asynchronous copies involve no register. Reads run at most 12 bytes past the slice plus the 28
 // prefetched ones (into the next start code); the ES blob carries 256 bytes of zero padding at its end.
 // ---------------------------------------------------------------------------------------------
+#if EF_K1A_ES16
+constexpr int kRingStride = kParseThreads * 16;         // bytes between the 16-byte chunk slots of one lane (4 slots)
+constexpr int kRingBytes = 4 * kRingStride;
+#else
 constexpr int kRingStride = kParseThreads * 4;          // bytes between ring slots of one lane: slot-major, conflict-free
 constexpr int kRingBytes = 8 * kRingStride;
+#endif
+constexpr int kStage = EF_K1A_STAGE;                    // list entries of the macroblock in flight staged per lane (row of kStage + 1 words)
+constexpr int kStageBytesA = kStage > 0 ? kParseThreads * (kStage + 1) * 4 : 0;
 
 struct BitReader {
     const uint32_t* words;   // the whole ES blob as aligned 32-bit words (cudaMalloc alignment)
     uint32_t rp;             // index of the next word to take from the ring
     uint32_t sring;          // shared-window address of this lane's ring slot 0
     uint32_t hi, lo;
+#if EF_K1A_RING_AHEAD || EF_K1A_ES16
+    uint32_t nx;             // raw word after `lo` (its ring load is issued one refill before it is needed: off the dependent chain)
+#endif
     int pos;
 
+#if EF_K1A_ES16
+    // 16-byte chunks: chunk c of the blob lives in slot c & 3. hi, lo, nx = words rp - 2, rp - 1, rp; the next word taken
+    // from the ring is rp + 1, in chunk (rp + 1) >> 2, and the chunks in flight always reach 3 past that one.
+    __device__ __forceinline__ void copy_chunk(uint32_t cidx)
+    {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sring + (cidx & 3u) * kRingStride), "l"((const uint4*)words + cidx) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void init(const uint8_t* blob, uint64_t byte_off)
+    {
+        words = (const uint32_t*)blob;
+        const uint32_t w0 = (uint32_t)(byte_off >> 2);
+        pos = (int)(byte_off & 3) * 8;
+        asm volatile("cp.async.wait_all;" ::: "memory");      // copies of the previous slice must not land in the new ring
+        rp = w0 + 2;
+        const uint32_t c0 = (rp + 1) >> 2;
+#pragma unroll
+        for (int k = 0; k < 4; k++) copy_chunk(c0 + k);
+        hi = __byte_perm(__ldg(words + w0), 0, 0x0123); lo = __byte_perm(__ldg(words + w0 + 1), 0, 0x0123);
+        nx = __ldg(words + w0 + 2);
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }
+    __device__ __forceinline__ void skip(int n)
+    {
+        pos += n;
+        if (pos >= 32) {
+            pos -= 32; hi = lo;
+            lo = __byte_perm(nx, 0, 0x0123);
+            rp++;
+            asm volatile("cp.async.wait_group 3;" ::: "memory");          // the chunk of word rp has landed (4 chunks in flight, one group each)
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nx) : "r"(sring + ((rp >> 2) & 3u) * kRingStride + (rp & 3u) * 4) : "memory");
+            if ((rp & 3u) == 3u) copy_chunk((rp >> 2) + 4);               // its last word: the slot takes the chunk 4 further on
+        }
+    }
+#else
     __device__ __forceinline__ void copy_in(uint32_t widx)
     {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sring + (widx & 7u) * kRingStride), "l"(words + widx) : "memory");
@@ -101,6 +147,9 @@ struct BitReader {
 #pragma unroll
         for (int k = 0; k < 7; k++) copy_in(rp + k);
         hi = __byte_perm(__ldg(words + w0), 0, 0x0123); lo = __byte_perm(__ldg(words + w0 + 1), 0, 0x0123);
+#if EF_K1A_RING_AHEAD
+        nx = __ldg(words + w0 + 2);
+#endif
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }
     __device__ __forceinline__ void skip(int n)
@@ -108,17 +157,25 @@ struct BitReader {
         pos += n;
         if (pos >= 32) {
             pos -= 32; hi = lo;
+#if EF_K1A_RING_AHEAD
+            lo = __byte_perm(nx, 0, 0x0123);
+            asm volatile("cp.async.wait_group 5;" ::: "memory");          // word rp + 1 has landed (7 copies in flight, one group each)
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nx) : "r"(sring + ((rp + 1) & 7u) * kRingStride) : "memory");
+            copy_in(rp + 7);                                              // slot (rp - 1) & 7: read one refill ago
+#else
             asm volatile("cp.async.wait_group 6;" ::: "memory");          // word rp has landed (7 copies in flight, one group each)
             uint32_t raw;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(sring + (rp & 7u) * kRingStride) : "memory");
             lo = __byte_perm(raw, 0, 0x0123);
             copy_in(rp + 7);                                              // into the slot that was read one refill ago
+#endif
 #if EF_K1A_PF_L2
             if ((rp & 7u) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(words + rp + 32));   // 128 bytes ahead of this slice's read position
 #endif
             rp++;
         }
     }
+#endif
     __device__ __forceinline__ uint32_t get(int n)     // 1 <= n <= 32
     {
         uint32_t v = peek() >> (32 - n);
@@ -132,6 +189,7 @@ struct SliceState {
     BitReader br;
     uint32_t* wptr;          // coefficient list of the macroblock in flight (HBM); entries are stored at wptr[cnt]
     uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture | destination frame store << 31
+    uint32_t seqi;           // index of the slice's sequence state in the stream's EfSeq table (K1a v3: handed to K1b for streams with their own matrices)
     const uint32_t* qz;      // scan-order quantiser | prescale | raster index tables [intra 64 | non-intra 64] of a stream with its OWN matrices (global memory); nullptr = the defaults, served from shared memory
     int mbw, mbh;
     int mb_x, mb_y;          // last macroblock handled
@@ -447,12 +505,11 @@ __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
 // table look-up); a symbol loop ends when no lane is busy or when kHdrBatch lanes are waiting.
 // =================================================================================================
 __global__ void __launch_bounds__(kParseThreads, kParseCtasPerSm)
-ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
+ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the context by value: every D.field is a constant-bank operand (no register, no load)
 {
-    extern __shared__ __align__(16) uint8_t smem[];           // tables | two-symbol table | bitstream rings
+    extern __shared__ __align__(16) uint8_t smem[];           // tables | two-symbol table | bitstream rings | staged list entries
     SharedTables& T = *(SharedTables*)smem;
     const uint2* lut = (const uint2*)(smem + kTableBytes);
-    const EfDev& D = *Dp;
     {   // stage the tables (the first sizeof(SharedTables) bytes of EfTables have the same layout)
         const uint32_t* src = (const uint32_t*)D.tables;
         uint32_t* dst = (uint32_t*)smem;
@@ -472,20 +529,38 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
 
     SliceState s;
     s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qz = nullptr; s.mbw = 0; s.mb_x = s.mb_y = 0;
-    s.br.sring = smem_u32(smem + kTableBytes + kLutBytes) + threadIdx.x * 4;
+    s.br.sring = smem_u32(smem + kTableBytes + kLutBytes) + threadIdx.x * (EF_K1A_ES16 ? 16 : 4);
+    // staged list entries: row of kStage + 1 words per lane (the odd stride spreads the rows over the banks)
+    const uint32_t sstage_warp = smem_u32(smem + kTableBytes + kLutBytes + kRingBytes) + (threadIdx.x & ~31u) * ((kStage + 1) * 4);
+    const uint32_t sstage = sstage_warp + lane * ((kStage + 1) * 4);
     bool active = false, exhausted = false, busy = false;
     // the macroblock in flight: info word under construction (bit 0 set = a record is owed), entry count |
     // skip run << 16, motion vector, record slot
     uint32_t info_acc = 0, cnt = 0, skipw = 0, mvw = 0, slot = 0;
-    uint32_t blk24 = 0, blkbit = 0;                           // current block: number << 24, 0x100 << number
+    uint32_t blk24 = 0, blkbit = 0;                           // current block: number << 24 (v3: token head = number << 27 | quantiser_scale << 16), 0x100 << number
     int cbp_rem = 0, n = 0, intra = 0, ctx = 0;               // n = scan position of the block in flight; ctx = 1: the next symbol is the first coefficient of a non-intra block
     // next coded block of the macroblock in flight (cbp_rem != 0): block number, contexts, intra DC
     auto start_block = [&]() {
         const int blk = __ffs(cbp_rem) - 1;
-        blk24 = (uint32_t)blk << 24; blkbit = 0x100u << blk;
+#if EF_K1B_DEQUANT
+        blk24 = ((uint32_t)blk << 27) | ((uint32_t)s.qscale << 16);
+#else
+        blk24 = (uint32_t)blk << 24;
+#endif
+        blkbit = 0x100u << blk;
         cbp_rem &= cbp_rem - 1;
         n = 0; ctx = 1;                                       // dct_coeff_first: no end of block, '1s' = (0, 1)
         if (intra) { D.mb_rec[slot].dc[blk] = parse_dc(s, blk); n = 1; ctx = 0; }
+    };
+    // list entry `cnt` of the macroblock in flight: staged in shared memory while it fits, else straight to the list in HBM
+    auto put_entry = [&](uint32_t ent) {
+#if EF_PROBE_NOSTORE                                                  /* bottleneck probe (wrong output): only entries nobody produces are stored */
+        if (ent == 0x12345678u) s.wptr[cnt] = ent;
+#else
+        if (kStage > 0 && cnt < (uint32_t)kStage) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sstage + cnt * 4), "r"(ent) : "memory");
+        else s.wptr[cnt] = ent;
+#endif
+        cnt++;
     };
     // first round: thread t takes slice t; afterwards lanes whose slice ended pull from the cursor
     const uint32_t first_round = gridDim.x * blockDim.x;
@@ -493,10 +568,31 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
 
     for (;;) {
         // ---- header phase: records of finished macroblocks ------------------------------------------
+        if (kStage > 0) {
+            // the staged head of every finished list goes out coalesced: lane j writes entry j of the list of lane `src`
+            __syncwarp();
+            const uint64_t li_mine = (uint64_t)(s.wptr - D.coef);
+            unsigned owed = __ballot_sync(0xFFFFFFFFu, !busy && (info_acc & 1u) && cnt != 0);
+            while (owed) {
+                const int src = __ffs(owed) - 1;
+                owed &= owed - 1;
+                const uint32_t c = min(__shfl_sync(0xFFFFFFFFu, cnt, src), (uint32_t)kStage);
+                const uint64_t lb = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)li_mine, src) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(li_mine >> 32), src) << 32);
+                for (uint32_t j = lane; j < c; j += 32) {
+                    uint32_t v;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sstage_warp + (uint32_t)src * ((kStage + 1) * 4) + j * 4) : "memory");
+                    D.coef[lb + j] = v;
+                }
+            }
+            __syncwarp();
+        }
         if (!busy && (info_acc & 1u)) {
             const uint64_t li = (uint64_t)(s.wptr - D.coef);
             *(uint4*)(D.mb_rec + slot) = make_uint4(cnt | (skipw << 16), mvw, (uint32_t)li, (uint32_t)(li >> 32));
             s.wptr += cnt;
+#if EF_K1B_DEQUANT
+            if (s.qz) { info_acc |= 1u << 26; D.mb_rec[slot].pad[0] = s.seqi; }     // K1b dequantises with the stream's own matrices
+#endif
             D.mb_info[slot] = info_acc | ((uint32_t)s.mbw << 20) | ((s.slot_base >> 31) << 25);
             info_acc = 0;
         }
@@ -525,6 +621,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                         s.mbw = min((int)seq->mb_width, EF_MBW_MAX);
                         s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
                         s.qz = seq->custom ? (const uint32_t*)seq->qz : nullptr;
+                        s.seqi = w.info >> 16;
                         const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
                         s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
                         s.slot_base |= ((D.base_pics[w.stream] + w.pic + 1u) & 1u) << 31;      // destination frame store: flush_picture(), player.cpp:692
@@ -558,6 +655,50 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
         // (one or two run/level codes with their sign bits, a closing '10') is taken in one step. Long codes,
         // the escape, invalid prefixes and symbols that would run past scan position 63 decode one symbol
         // through the clz-indexed table (and fold a following end of block in).
+#if EF_K1A_V3
+        // ---- symbol loop, v3: per busy lane and step ONE run/level symbol through the clz-indexed table, a following
+        // end of block folded in; dequantised on the spot (table word of the scan position: shared memory for the default
+        // matrices, the stream's own table in HBM otherwise) or, with EF_K1B_DEQUANT, stored as a raw token
+        const int qoff = intra ? 0 : 64, kq = intra ? 0 : 1;
+        for (;;) {
+            const unsigned bmask = __ballot_sync(0xFFFFFFFFu, busy);
+            if (!bmask) break;
+            if (kHdrBatch < 32 && __popc(__ballot_sync(0xFFFFFFFFu, active && !busy)) >= kHdrBatch) break;
+            if (busy) {
+                BitReader& br = s.br;
+                const uint32_t w = br.peek();
+                const EfSym sy = ef_coef_sym(w, ctx != 0, T.dct);
+                ctx = 0;
+                int len = sy.len;
+                bool block_done = sy.kind == EF_SYM_EOB;
+                if (sy.kind == EF_SYM_DERAIL) {                  // give up on this and the remaining blocks, end the slice
+                    info_acc |= (blkbit << 6) | ((uint32_t)cbp_rem << 14);
+                    s.mb_y = s.mbh;
+                    busy = false;
+                } else {
+                    if (sy.kind == EF_SYM_COEF) {
+                        n += sy.run;
+                        if (n > 63) { info_acc |= blkbit << 6; block_done = true; }      // block() returns -1: nothing of the block is stored; the symbol is consumed
+                        else {
+#if EF_K1B_DEQUANT
+                            put_entry(blk24 | ((uint32_t)n << 21) | ((uint32_t)sy.lvl & 0xFFFFu));
+#else
+                            put_entry(ef_coef_entry(s.qz ? __ldg(s.qz + qoff + n) : T.qz[qoff + n], sy.lvl, s.qscale, kq, blk24));
+#endif
+                            n++;
+                            if (len <= 30 && ((w << len) >> 30) == 2u) { len += 2; block_done = true; }   // '10' follows: end of block
+                        }
+                    }
+                    br.skip(len);
+                    if (block_done) {
+                        if (n == 1) info_acc |= blkbit;          // Q5 (an aborted block has n >= 64)
+                        busy = cbp_rem != 0;
+                        if (busy) start_block();
+                    }
+                }
+            }
+        }
+#else
         const int qoff = intra ? 0 : 64;
         const int kq = intra ? 0 : 1;
         // table word of scan position n: shared memory for the default matrices (no global-load latency in the symbol
@@ -574,8 +715,8 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                 const uint32_t fl = st.fl;
                 const int len = st.len;
                 ctx = 0;
-                if (fl & EF_STEP_COEF1) { n += st.run1; s.wptr[cnt++] = ef_coef_entry(qword(n), st.lvl1, s.qscale, kq, blk24); n++; }
-                if (fl & EF_STEP_COEF2) { n += st.run2; s.wptr[cnt++] = ef_coef_entry(qword(n), st.lvl2, s.qscale, kq, blk24); n++; }
+                if (fl & EF_STEP_COEF1) { n += st.run1; put_entry(ef_coef_entry(qword(n), st.lvl1, s.qscale, kq, blk24)); n++; }
+                if (fl & EF_STEP_COEF2) { n += st.run2; put_entry(ef_coef_entry(qword(n), st.lvl2, s.qscale, kq, blk24)); n++; }
                 if (fl & 16u) {                                // give up on this and the remaining blocks, end the slice
                     info_acc |= (blkbit << 6) | ((uint32_t)cbp_rem << 14);
                     s.mb_y = s.mbh;
@@ -591,6 +732,7 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
                 }
             }
         }
+#endif
     }
 }
 
@@ -604,10 +746,9 @@ ef_parse_kernel(const EfDev* __restrict__ Dp, int pic0, int n_pics)
 //                                   row pass 2:    chroma plane hl/8 (block 4 + hl/8), row hl%8
 // =================================================================================================
 __global__ void __launch_bounds__(kReconWarps * 32, kReconCtasPerSm)
-ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
+ef_recon_kernel(const __grid_constant__ EfDev D, int pic_rel)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    const EfDev& D = *Dp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int hl = lane & 15, hb = lane & 16, half = lane >> 4;
     uint8_t* wbase = smem + (size_t)warp * kWarpBytes;
@@ -618,6 +759,11 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
     uint32_t bar_phase = 0;
     if (hl == 0) mbar_init(bar, 1);
     for (int i = hl; i < kDenseWords; i += 16) dense[i] = 0;
+#if EF_K1B_DEQUANT
+    const uint32_t* qzs = (const uint32_t*)(smem + (size_t)kReconWarps * kWarpBytes);   // default matrices: quantiser | prescale << 8 | raster index << 18 per scan position
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) ((uint32_t*)qzs)[i] = D.tables->qz[i];
+    __syncthreads();
+#endif
     __syncwarp();
 
     constexpr uint32_t kMbs = EF_MBW_MAX * EF_MBH_MAX;
@@ -632,7 +778,7 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
     // one load per lane fetches a record: lanes 0-9 of the half its words, lane 12 the info word
     auto fetch = [&](uint32_t slot) -> uint32_t {
         uint32_t v = 0;
-        if (slot < n_slots && (hl < 10 || hl == 12)) v = __ldg(hl == 12 ? infos + slot : recs + (size_t)slot * (sizeof(EfMbRec) / 4) + hl);
+        if (slot < n_slots && (hl < (EF_K1B_DEQUANT ? 11 : 10) || hl == 12)) v = __ldg(hl == 12 ? infos + slot : recs + (size_t)slot * (sizeof(EfMbRec) / 4) + hl);
         return v;
     };
 
@@ -707,8 +853,20 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
         }
 
         // expand the coefficient list into the dense scratch (entries of aborted blocks are dropped)
+#if EF_K1B_DEQUANT
+        // token = block << 27 | scan position << 21 | quantiser_scale << 16 | (int16) level: dequantise here (block(),
+        // player.cpp:1106-1121), with the table word of the scan position from shared memory (default matrices) or from
+        // the stream's sequence state (info bit 26; record word 10 = its index)
+        const int qoff = intra_r ? 0 : 64, kq = intra_r ? 0 : 1;
+        const uint32_t seqi = __shfl_sync(0xFFFFFFFFu, recw, hb + 10);
+        const uint32_t* cqz = nullptr;
+        if (valid && ((info >> 26) & 1u)) cqz = D.seq[(size_t)stream * (D.max_seq + 1) + min(seqi, (uint32_t)D.max_seq)].qz;
+#define EF_EXPAND(ent) { const uint32_t t_ = (ent); const int eb = (t_ >> 27) & 7; if (!((abm >> eb) & 1)) { const int n_ = qoff + ((t_ >> 21) & 63); \
+            const uint32_t z_ = cqz ? __ldg(cqz + n_) : qzs[n_]; dense[eb * kDenseStride + ((z_ >> 18) & 63)] = ef_dequant(z_, (int)(int16_t)(t_ & 0xFFFFu), (int)((t_ >> 16) & 31u), kq); } }
+#else
         // entry = (block << 24 | raster position << 18) + value, |value| < 2^17: adding 2^17 undoes the borrow of a negative value
 #define EF_EXPAND(ent) { const uint32_t hi_ = (ent) + 0x20000u; const int eb = (hi_ >> 24) & 7; if (!((abm >> eb) & 1)) dense[eb * kDenseStride + ((hi_ >> 18) & 63)] = ((int)((ent) << 14)) >> 14; }
+#endif
         if (hl < entries) EF_EXPAND(e0)
         if (hl + 16 < entries) EF_EXPAND(e1)
         if (hl + 32 < entries) EF_EXPAND(e2)
@@ -798,8 +956,8 @@ ef_recon_kernel(const EfDev* __restrict__ Dp, int pic_rel)
 }
 
 // host-side launch helpers -----------------------------------------------------------------------
-size_t ef_recon_smem_bytes() { return (size_t)kReconWarps * kWarpBytes; }
-static constexpr size_t kParseSmemBytes = (size_t)kTableBytes + kLutBytes + kRingBytes;
+size_t ef_recon_smem_bytes() { return (size_t)kReconWarps * kWarpBytes + kReconQzBytes; }
+static constexpr size_t kParseSmemBytes = (size_t)kTableBytes + kLutBytes + kRingBytes + kStageBytesA;
 
 static int g_parse_ctas = kParseCtasPerSm, g_recon_ctas = kReconCtasPerSm;   // resident CTAs per SM, measured by the occupancy API
 
@@ -827,7 +985,7 @@ int ef_decode_resident_ctas(int which) { return which == 0 ? g_parse_ctas : g_re
 // parse every slice of picture indices [pic0, pic0 + n_pics) into record pictures 0 .. n_pics-1
 // (grids are persistent - one wave of resident CTAs - but never larger than the work: a one-stream context of the
 // level-1 drop-in launches a handful of CTAs, not 592 that each stage 20 KB of tables first)
-cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count, size_t max_slices, cudaStream_t stream)
+cudaError_t ef_launch_parse(const EfDev& dev, int pic0, int n_pics, int sm_count, size_t max_slices, cudaStream_t stream)
 {
     size_t grid = (size_t)sm_count * g_parse_ctas, need = (max_slices + kParseThreads - 1) / kParseThreads;
     if (need < 1) need = 1;
@@ -837,7 +995,7 @@ cudaError_t ef_launch_parse(const EfDev* dev, int pic0, int n_pics, int sm_count
 }
 
 // rebuild one picture index of every stream from record picture `pic_rel`
-cudaError_t ef_launch_recon(const EfDev* dev, int pic_rel, int sm_count, size_t n_slots, cudaStream_t stream)
+cudaError_t ef_launch_recon(const EfDev& dev, int pic_rel, int sm_count, size_t n_slots, cudaStream_t stream)
 {
     size_t grid = (size_t)sm_count * g_recon_ctas, need = (n_slots / 2 + kReconWarps - 1) / kReconWarps;
     if (need < 1) need = 1;

@@ -86,6 +86,35 @@ static Result model_block(const EfTables& T, const Bits& B, size_t pos, bool non
     return r;
 }
 
+// K1a v3: one symbol per step (ef_coef_sym), a following '10' folded in by the caller exactly as the kernel does
+static Result model_block_v3(const EfTables& T, const Bits& B, size_t pos, bool nonintra)
+{
+    Result r; r.end = 2;
+    int n = nonintra ? 0 : 1;
+    bool first = nonintra;
+    for (int guard = 0; guard < 200; guard++) {
+        const uint32_t w = B.window(pos);
+        const EfSym s = ef_coef_sym(w, first, T.dct);
+        first = false;
+        if (s.kind == EF_SYM_DERAIL) { r.end = 2; break; }
+        int len = s.len;
+        bool done = s.kind == EF_SYM_EOB;
+        if (s.kind == EF_SYM_COEF) {
+            n += s.run;
+            if (n > 63) { pos += len; r.end = 1; break; }
+            // through the token, as K1b reads it back
+            const uint32_t tok = ef_token(5u, n, 31, s.lvl);
+            r.c.push_back({ (int)((tok >> 21) & 63u), (int)(int16_t)(tok & 0xFFFFu) });
+            n++;
+            if (len <= 30 && ((w << len) >> 30) == 2u) { len += 2; done = true; }
+        }
+        pos += len;
+        if (done) { r.end = 0; break; }
+    }
+    r.bits = pos;
+    return r;
+}
+
 static long n_blocks = 0, n_coefs = 0, n_steps_saved = 0;
 static int compare(const EfTables& T, const Bits& B, size_t pos, bool nonintra, const char* what)
 {
@@ -93,6 +122,14 @@ static int compare(const EfTables& T, const Bits& B, size_t pos, bool nonintra, 
     n_blocks++; n_coefs += (long)a.c.size();
     bool ok = a.end == m.end && a.c.size() == m.c.size() && (a.end == 2 || a.bits == m.bits);
     for (size_t i = 0; ok && i < a.c.size(); i++) ok = a.c[i].pos == m.c[i].pos && a.c[i].level == m.c[i].level;
+    const Result v3 = model_block_v3(T, B, pos, nonintra);
+    bool ok3 = a.end == v3.end && a.c.size() == v3.c.size() && (a.end == 2 || a.bits == v3.bits);
+    for (size_t i = 0; ok3 && i < a.c.size(); i++) ok3 = a.c[i].pos == v3.c[i].pos && a.c[i].level == v3.c[i].level;
+    if (!ok3) {
+        fprintf(stderr, "V3 MISMATCH (%s, %s): ref end %d coefs %zu bits %zu / v3 end %d coefs %zu bits %zu\n", what, nonintra ? "non-intra" : "intra",
+                a.end, a.c.size(), a.bits - pos, v3.end, v3.c.size(), v3.bits - pos);
+        return 1;
+    }
     if (!ok) {
         fprintf(stderr, "MISMATCH (%s, %s): ref end %d coefs %zu bits %zu / model end %d coefs %zu bits %zu\n", what, nonintra ? "non-intra" : "intra",
                 a.end, a.c.size(), a.bits - pos, m.end, m.c.size(), m.bits - pos);
@@ -169,6 +206,9 @@ int main()
                 const uint32_t ent = ef_coef_entry(z, level, qs, k, blk << 24);
                 const uint32_t hi = ent + 0x20000u;
                 const int got = ((int)(ent << 14)) >> 14, gb = (hi >> 24) & 7, gp = (hi >> 18) & 63;
+                const uint32_t tok = ef_token(blk, n & 63, qs, level);               // v3: token -> K1b's dequantisation
+                const int got3 = ef_dequant(T.qz[(intra ? 0 : 64) + (int)((tok >> 21) & 63u)], (int)(int16_t)(tok & 0xFFFFu), (int)((tok >> 16) & 31u), k);
+                if (got3 != want || (tok >> 27) != blk) { fprintf(stderr, "TOKEN MISMATCH n %d level %d qs %d: want %d got %d\n", n, level, qs, want, got3); bad++; }
                 if (got != want || gb != (int)blk || gp != zz) {
                     fprintf(stderr, "ENTRY MISMATCH n %d level %d qs %d: want %d blk %u pos %d, got %d blk %d pos %d\n", n, level, qs, want, blk, zz, got, gb, gp);
                     bad++;
