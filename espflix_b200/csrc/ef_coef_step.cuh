@@ -108,9 +108,11 @@ struct EfSym {
 static __host__ __device__ __forceinline__ EfSym ef_coef_sym(uint32_t w, bool first, const uint16_t* __restrict__ dct)
 {
     EfSym r;
-    const int lz = EF_CLZ(w);
-    // row (context, leading zeros), column = the five bits after the leading one; row 12 is all-invalid (>= 12 zeros)
-    const int idx = w >= 0x00100000u ? (first ? 13 * 32 - 32 : -32) + lz * 32 + (int)((w << (lz & 31)) >> 26) : 12 * 32;
+    // row (context, leading zeros), column = the five bits after the leading one. Branch-free: the row saturates at 12
+    // (all-invalid: >= 12 leading zeros is not a code) and the leading-one column bit is forced, so that a window with
+    // more than 12 zeros cannot slide back into row 11
+    const int lz = EF_CLZ(w), row = lz < 12 ? lz : 12;
+    const int idx = (first ? 13 * 32 - 32 : -32) + row * 32 + (int)(((w << row) >> 26) | 32u);
     const uint32_t t = dct[idx];
     r.len = (int)(t & 31u); r.run = (int)((t >> 5) & 31u);
     const int mag = (int)(t >> 10);

@@ -57,6 +57,9 @@
 #ifndef EF_K1A_STAGE
 #define EF_K1A_STAGE 32          // K1a: the first N list entries of a macroblock are staged in shared memory and written out by the whole warp, coalesced, when the
 #endif                           //      macroblock is complete (0: every entry is its own scattered 4-byte store)
+#ifndef EF_K1A_UNROLL
+#define EF_K1A_UNROLL 3          // K1a v3: symbol steps per pass of the loop (one vote + branch per pass)
+#endif
 #ifndef EF_PROBE_NOSTORE
 #define EF_PROBE_NOSTORE 0       // measurement probe only: K1a drops its coefficient stores (output wrong)
 #endif

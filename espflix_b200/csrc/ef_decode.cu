@@ -190,6 +190,7 @@ struct SliceState {
     uint32_t* wptr;          // coefficient list of the macroblock in flight (HBM); entries are stored at wptr[cnt]
     uint32_t slot_base;      // record slot of macroblock (0,0) of this slice's picture | destination frame store << 31
     uint32_t seqi;           // index of the slice's sequence state in the stream's EfSeq table (K1a v3: handed to K1b for streams with their own matrices)
+    const uint32_t* qzp;     // generic pointer to the table words in use: T.qz in shared memory (default matrices) or the stream's own in HBM
     const uint32_t* qz;      // scan-order quantiser | prescale | raster index tables [intra 64 | non-intra 64] of a stream with its OWN matrices (global memory); nullptr = the defaults, served from shared memory
     int mbw, mbh;
     int mb_x, mb_y;          // last macroblock handled
@@ -622,6 +623,7 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
                         s.mbh = min((int)seq->mb_height, EF_MBH_MAX);
                         s.qz = seq->custom ? (const uint32_t*)seq->qz : nullptr;
                         s.seqi = w.info >> 16;
+                        s.qzp = s.qz ? s.qz : T.qz;
                         const uint64_t byte_off = D.es_off[w.stream] + w.es_off;
                         s.slot_base = (w.pic - (uint32_t)pic0) * n_slots + w.stream * (uint32_t)(EF_MBW_MAX * EF_MBH_MAX);
                         s.slot_base |= ((D.base_pics[w.stream] + w.pic + 1u) & 1u) << 31;      // destination frame store: flush_picture(), player.cpp:692
@@ -664,6 +666,8 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
             const unsigned bmask = __ballot_sync(0xFFFFFFFFu, busy);
             if (!bmask) break;
             if (kHdrBatch < 32 && __popc(__ballot_sync(0xFFFFFFFFu, active && !busy)) >= kHdrBatch) break;
+#pragma unroll
+            for (int u_ = 0; u_ < EF_K1A_UNROLL; u_++)
             if (busy) {
                 BitReader& br = s.br;
                 const uint32_t w = br.peek();
@@ -683,7 +687,7 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
 #if EF_K1B_DEQUANT
                             put_entry(blk24 | ((uint32_t)n << 21) | ((uint32_t)sy.lvl & 0xFFFFu));
 #else
-                            put_entry(ef_coef_entry(s.qz ? __ldg(s.qz + qoff + n) : T.qz[qoff + n], sy.lvl, s.qscale, kq, blk24));
+                            put_entry(ef_coef_entry(s.qzp[qoff + n], sy.lvl, s.qscale, kq, blk24));
 #endif
                             n++;
                             if (len <= 30 && ((w << len) >> 30) == 2u) { len += 2; block_done = true; }   // '10' follows: end of block
