@@ -80,15 +80,24 @@ struct DeviceScope {
 // luma tile rows are 16 bytes, chroma tile rows 8, and 352, 176 and 528 are multiples of 8).
 // fb_sel: 0 / 1 = that frame store; -1 = the most recent picture of each stream; -2 - p = picture p of the current
 // submit (the store flush_picture() gave it, player.cpp:692)
+// fb_snap (optional, fb_sel == -1): the frame store of every stream's most recent picture, frozen by ef_latest_fb_kernel
+// when the read-back was requested (the export itself may run while the next submit is already being indexed)
+__global__ void ef_latest_fb_kernel(const uint32_t* __restrict__ base_pics, const uint32_t* __restrict__ n_pics, int first, int count, uint8_t* __restrict__ fb_snap)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) fb_snap[k] = (uint8_t)((base_pics[first + k] + n_pics[first + k]) & 1u);
+}
+
 __global__ void ef_export_frames_kernel(const uint8_t* __restrict__ frames, const uint32_t* __restrict__ base_pics,
-                                        const uint32_t* __restrict__ n_pics, int first, int count, int fb_sel, int mode, uint8_t* __restrict__ dst)
+                                        const uint32_t* __restrict__ n_pics, int first, int count, int fb_sel, int mode, uint8_t* __restrict__ dst,
+                                        const uint8_t* __restrict__ fb_snap = nullptr)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t per = EF_FRAME / 8;
     const uint32_t k = (uint32_t)(t / per), w = (uint32_t)(t % per);
     if (k >= (uint32_t)count) return;
     const int s = first + (int)k;
-    const int fb = fb_sel >= 0 ? fb_sel : fb_sel == -1 ? (int)((base_pics[s] + n_pics[s]) & 1u) : (int)((base_pics[s] + (uint32_t)(-2 - fb_sel) + 1u) & 1u);
+    const int fb = fb_sel >= 0 ? fb_sel : fb_sel == -1 ? (fb_snap ? (int)fb_snap[k] : (int)((base_pics[s] + n_pics[s]) & 1u)) : (int)((base_pics[s] + (uint32_t)(-2 - fb_sel) + 1u) & 1u);
     const uint8_t* f = frames + ef_frame_offset(s, fb);
     const int b = (int)w * 8;
     const int src = mode == 0 ? ef_i420_to_tiled(b) : ef_strips_to_tiled(b);
@@ -134,6 +143,9 @@ struct ef_ctx {
     cudaStream_t up_stream = nullptr, down_stream = nullptr;
     cudaEvent_t ev_user = nullptr, ev_up_done[2] = { nullptr, nullptr }, ev_buf_free[2] = { nullptr, nullptr };
     cudaEvent_t ev_export = nullptr, ev_down_done[2] = { nullptr, nullptr };
+    uint8_t* d_fb_snap[2] = { nullptr, nullptr };  // per staging buffer: frame store of every stream's latest picture at request time
+    cudaEvent_t ev_frames_read = nullptr;         // the asynchronous read-back has finished reading the frame stores (its export kernel runs on the read-back stream)
+    bool frames_read_pending = false;
     uint8_t* d_stage2[2] = { nullptr, nullptr };  // read-back staging of ef_read_latest_i420(_async), alternating
     size_t stage2_bytes[2] = { 0, 0 };
     int stage_idx = 0;
@@ -258,6 +270,7 @@ int ef_create(ef_ctx** out, const ef_config* cfg)
     }
     CK(cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_export, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_frames_read, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
     A(h.frames, (size_t)n * 2 * EF_FRAME + 1024);
@@ -326,6 +339,7 @@ void ef_destroy(ef_ctx* c)
     for (int i = 0; i < 5; i++) if (c->ev_prof[i]) cudaEventDestroy(c->ev_prof[i]);
     if (c->ev_user) cudaEventDestroy(c->ev_user);
     if (c->ev_export) cudaEventDestroy(c->ev_export);
+    if (c->ev_frames_read) cudaEventDestroy(c->ev_frames_read);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
     delete c;
@@ -501,6 +515,7 @@ static int decode_range(ef_ctx* c, int p0, int k, cudaStream_t st, uint8_t* host
     CK(ef_launch_parse(dev, p0, k, c->sm_count, (size_t)k * c->cfg.n_streams * c->cfg.max_slices_per_picture, st));
     if (c->profiling) CK(cudaEventRecord(c->ev_prof[3], st));
     const size_t batch_bytes = (size_t)c->cfg.n_streams * EF_FRAME;
+    if (c->frames_read_pending) { CK(cudaStreamWaitEvent(st, c->ev_frames_read, 0)); c->frames_read_pending = false; }   // an asynchronous read-back still reads the frame stores
     for (int i = 0; i < k; i++) {
         CK(ef_launch_recon(dev, i, c->sm_count, (size_t)c->cfg.n_streams * EF_MBW_MAX * EF_MBH_MAX, st));
         if (host_dst) {
@@ -584,13 +599,21 @@ int ef_read_latest_i420_async(ef_ctx* c, int first, int count, uint8_t* dst, voi
     const size_t bytes = (size_t)count * EF_FRAME;
     { int rc = ensure_stage2(c, k, bytes); if (rc != EF_OK) return rc; }
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaStreamWaitEvent(st, c->ev_down_done[k], 0));        // the previous copy out of this staging buffer has finished
-    const uint64_t threads = (uint64_t)count * (EF_FRAME / 8);
-    ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, 0, c->d_stage2[k]);
+    // The tiled -> I420 export runs on the read-back stream, behind everything queued on the caller's stream so far and
+    // behind the previous copy out of this staging buffer: it overlaps the index / parse kernels of the next submit. The
+    // next reconstruction launch (the first thing that writes a frame store again) waits for ev_frames_read.
+    if (!c->d_fb_snap[k]) { int rc = dev_alloc(c, &c->d_fb_snap[k], (size_t)c->cfg.n_streams); if (rc != EF_OK) return rc; }
+    CK(cudaStreamWaitEvent(st, c->ev_down_done[k], 0));        // the previous read-back through this staging buffer (and its snapshot) has finished
+    ef_latest_fb_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(c->h.base_pics, c->h.n_pics, first, count, c->d_fb_snap[k]);
     CK(cudaGetLastError());
-    c->launches++;
     CK(cudaEventRecord(c->ev_export, st));
     CK(cudaStreamWaitEvent(c->down_stream, c->ev_export, 0));
+    const uint64_t threads = (uint64_t)count * (EF_FRAME / 8);
+    ef_export_frames_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->down_stream>>>(c->h.frames, c->h.base_pics, c->h.n_pics, first, count, -1, 0, c->d_stage2[k], c->d_fb_snap[k]);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaEventRecord(c->ev_frames_read, c->down_stream));
+    c->frames_read_pending = true;
     CK(cudaMemcpyAsync(dst, c->d_stage2[k], bytes, cudaMemcpyDeviceToHost, c->down_stream));   // overlaps the next decode when dst is pinned
     CK(cudaEventRecord(c->ev_down_done[k], c->down_stream));
     return EF_OK;

@@ -84,6 +84,7 @@ constexpr int kRingBytes = 4 * kRingStride;
 constexpr int kRingStride = kParseThreads * 4;          // bytes between ring slots of one lane: slot-major, conflict-free
 constexpr int kRingBytes = 8 * kRingStride;
 #endif
+constexpr int kFlushUnroll = EF_K1A_FLUSH_UNROLL;
 constexpr int kStage = EF_K1A_STAGE;                    // list entries of the macroblock in flight staged per lane (row of kStage + 1 words)
 constexpr int kStageBytesA = kStage > 0 ? kParseThreads * (kStage + 1) * 4 : 0;
 
@@ -573,16 +574,34 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
             // the staged head of every finished list goes out coalesced: lane j writes entry j of the list of lane `src`
             __syncwarp();
             const uint64_t li_mine = (uint64_t)(s.wptr - D.coef);
-            unsigned owed = __ballot_sync(0xFFFFFFFFu, !busy && (info_acc & 1u) && cnt != 0);
-            while (owed) {
-                const int src = __ffs(owed) - 1;
-                owed &= owed - 1;
-                const uint32_t c = min(__shfl_sync(0xFFFFFFFFu, cnt, src), (uint32_t)kStage);
-                const uint64_t lb = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)li_mine, src) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(li_mine >> 32), src) << 32);
-                for (uint32_t j = lane; j < c; j += 32) {
-                    uint32_t v;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sstage_warp + (uint32_t)src * ((kStage + 1) * 4) + j * 4) : "memory");
-                    D.coef[lb + j] = v;
+            if (kStage <= 32 && kHdrBatch == 32) {
+                // every lane is between macroblocks: a fixed walk over the 32 lists, the source lane an immediate
+                const uint32_t c_mine = (!busy && (info_acc & 1u)) ? min(cnt, (uint32_t)kStage) : 0u;
+                if (__any_sync(0xFFFFFFFFu, c_mine != 0)) {
+                    const uint32_t srow = sstage_warp + lane * 4;
+#pragma unroll (kFlushUnroll)
+                    for (int src = 0; src < 32; src++) {
+                        const uint32_t c = __shfl_sync(0xFFFFFFFFu, c_mine, src);
+                        const uint64_t lb = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)li_mine, src) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(li_mine >> 32), src) << 32);
+                        if (lane < c) {
+                            uint32_t v;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(srow + (uint32_t)src * ((kStage + 1) * 4)) : "memory");
+                            D.coef[lb + lane] = v;
+                        }
+                    }
+                }
+            } else {
+                unsigned owed = __ballot_sync(0xFFFFFFFFu, !busy && (info_acc & 1u) && cnt != 0);
+                while (owed) {
+                    const int src = __ffs(owed) - 1;
+                    owed &= owed - 1;
+                    const uint32_t c = min(__shfl_sync(0xFFFFFFFFu, cnt, src), (uint32_t)kStage);
+                    const uint64_t lb = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)li_mine, src) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(li_mine >> 32), src) << 32);
+                    for (uint32_t j = lane; j < c; j += 32) {
+                        uint32_t v;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sstage_warp + (uint32_t)src * ((kStage + 1) * 4) + j * 4) : "memory");
+                        D.coef[lb + j] = v;
+                    }
                 }
             }
             __syncwarp();
