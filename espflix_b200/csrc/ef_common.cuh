@@ -61,7 +61,7 @@
 #define EF_K1A_UNROLL 3          // K1a v3: symbol steps per pass of the loop (one vote + branch per pass)
 #endif
 #ifndef EF_K1A_FLUSH_UNROLL
-#define EF_K1A_FLUSH_UNROLL 2    // K1a: source lanes per pass of the staged-list flush
+#define EF_K1A_FLUSH_UNROLL 4    // K1a: source lanes per pass of the staged-list flush
 #endif
 #ifndef EF_PROBE_NOSTORE
 #define EF_PROBE_NOSTORE 0       // measurement probe only: K1a drops its coefficient stores (output wrong)

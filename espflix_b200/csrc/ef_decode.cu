@@ -18,6 +18,11 @@
 //       (quirk Q2 included) happens on the spot. The list of a slice starts at entry 3 x (byte offset
 //       of the slice in the ES blob): every coefficient costs at least 3 bits of bitstream, so lists
 //       can never run into each other and no allocation or prefix sum is needed.
+//       A global-memory instruction whose lanes point into 32 different slices costs the load/store
+//       unit a cycle per lane, and the round-1 parser issued two of them per symbol step; so the
+//       bitstream comes in as 16-byte cp.async.cg chunks (one per lane per 128 bits) and the first 32
+//       list entries of a macroblock are staged in shared memory and written out by the whole warp,
+//       one list per store instruction, when the macroblock is complete.
 //   K1b ef_recon_kernel   records -> pixels, one launch per picture index (P pictures read the
 //       previous picture of their stream). One HALF-WARP per macroblock record (a warp = two
 //       consecutive slots), all 1,081,344 of a BASELINE picture batch independent: scatter the list
@@ -503,8 +508,9 @@ __device__ __forceinline__ int parse_dc(SliceState& s, int blk)
 //
 // Lane states: no slice (idle / exhausted), WAITING for the header of its next macroblock, BUSY in the
 // coefficient state machine. Header phases (flush finished records, refill idle lanes, parse headers)
-// alternate with symbol loops (per busy lane and step: up to two coefficients and an end of block from one
-// table look-up); a symbol loop ends when no lane is busy or when kHdrBatch lanes are waiting.
+// alternate with symbol loops (per busy lane and step: one run/level symbol with a following end of block folded in -
+// or, with EF_K1A_V3 = 0, up to two coefficients and an end of block from one look-up in the two-symbol table); a
+// symbol loop ends when no lane is busy or when kHdrBatch lanes are waiting.
 // =================================================================================================
 __global__ void __launch_bounds__(kParseThreads, kParseCtasPerSm)
 ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the context by value: every D.field is a constant-bank operand (no register, no load)
