@@ -345,10 +345,18 @@ void ef_destroy(ef_ctx* c)
     delete c;
 }
 
+// an asynchronous read-back may still be reading the frame stores on the read-back stream: host-driven writers wait for it
+static int wait_frames_read(ef_ctx* c)
+{
+    if (c->frames_read_pending) { CK(cudaEventSynchronize(c->ev_frames_read)); c->frames_read_pending = false; }
+    return EF_OK;
+}
+
 int ef_reset(ef_ctx* c)
 {
     DeviceScope scope_(c ? c->cfg.device : -1);
     if (!c) return fail(EF_EINVAL, "null context");
+    { int rcw = wait_frames_read(c); if (rcw != EF_OK) return rcw; }
     CK(cudaMemset(c->h.frames, 0, (size_t)c->cfg.n_streams * 2 * EF_FRAME + 1024));     // Frame::init zero-fills (player.cpp:25)
     ef_reset_seq_kernel<<<(c->cfg.n_streams + 127) / 128, 128>>>(c->d, c->d_default_intra);
     CK(cudaGetLastError());
@@ -661,6 +669,7 @@ int ef_write_frame_i420(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
     if (rc != EF_OK) return rc;
     rc = ensure_stage(c, EF_FRAME);
     if (rc != EF_OK) return rc;
+    if ((rc = wait_frames_read(c)) != EF_OK) return rc;
     CK(cudaMemcpy(c->d_stage, src, EF_FRAME, cudaMemcpyHostToDevice));
     ef_import_frame_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames + ef_frame_offset(stream_index, f), c->d_stage, 0);
     CK(cudaGetLastError());
@@ -677,6 +686,7 @@ int ef_write_frame(ef_ctx* c, int stream_index, int fb, const uint8_t* src)
     if (rc != EF_OK) return rc;
     rc = ensure_stage(c, EF_FRAME);
     if (rc != EF_OK) return rc;
+    if ((rc = wait_frames_read(c)) != EF_OK) return rc;
     CK(cudaMemcpy(c->d_stage, src, EF_FRAME, cudaMemcpyHostToDevice));
     ef_import_frame_kernel<<<(EF_FRAME / 4 + 255) / 256, 256>>>(c->h.frames + ef_frame_offset(stream_index, f), c->d_stage, 1);
     CK(cudaGetLastError());

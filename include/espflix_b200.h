@@ -129,7 +129,9 @@ int ef_write_frame(ef_ctx* ctx, int stream_index, int fb, const uint8_t* src_str
 int ef_frame_device_ptr(ef_ctx* ctx, int stream_index, int fb, void** ptr);
 /* Batched read-back of the most recent picture of streams [first, first+count) as I420. The _async form
  * returns once the copy is queued (dst should be pinned; it is complete after ef_sync) so that it overlaps
- * the next submit/decode; the plain form waits for it. */
+ * the next submit/decode; the plain form waits for it. Which picture is "most recent" is frozen when the call is made;
+ * the library orders the read against everything that writes a frame store afterwards (the next decode, ef_write_frame,
+ * ef_reset). */
 int ef_read_latest_i420(ef_ctx* ctx, int first, int count, uint8_t* dst, void* stream);
 int ef_read_latest_i420_async(ef_ctx* ctx, int first, int count, uint8_t* dst, void* stream);
 /* Wait for `stream` and for the context's internal upload / read-back streams. */
