@@ -90,8 +90,12 @@ constexpr int kRingStride = kParseThreads * 4;          // bytes between ring sl
 constexpr int kRingBytes = 8 * kRingStride;
 #endif
 constexpr int kFlushUnroll = EF_K1A_FLUSH_UNROLL;
-constexpr int kStage = EF_K1A_STAGE;                    // list entries of the macroblock in flight staged per lane (row of kStage + 1 words)
-constexpr int kStageBytesA = kStage > 0 ? kParseThreads * (kStage + 1) * 4 : 0;
+constexpr int kStage = EF_K1A_STAGE;                    // list entries of the macroblock in flight staged per lane
+// bytes per staging row: with the 16-byte bitstream slots a multiple of 16 (36 words for 32 entries), so that a lane's row
+// address is a multiple of its ring address (one IMAD where the compiler otherwise re-derives it from the thread index at
+// every store); else an odd number of words
+constexpr int kStageRow = EF_K1A_ES16 ? ((kStage * 4 + 16 + 15) & ~15) : (kStage + 1) * 4;
+constexpr int kStageBytesA = kStage > 0 ? kParseThreads * kStageRow : 0;
 
 struct BitReader {
     const uint32_t* words;   // the whole ES blob as aligned 32-bit words (cudaMalloc alignment)
@@ -538,9 +542,15 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
     SliceState s;
     s.first = 0; s.wptr = nullptr; s.slot_base = 0; s.qz = nullptr; s.mbw = 0; s.mb_x = s.mb_y = 0;
     s.br.sring = smem_u32(smem + kTableBytes + kLutBytes) + threadIdx.x * (EF_K1A_ES16 ? 16 : 4);
-    // staged list entries: row of kStage + 1 words per lane (the odd stride spreads the rows over the banks)
-    const uint32_t sstage_warp = smem_u32(smem + kTableBytes + kLutBytes + kRingBytes) + (threadIdx.x & ~31u) * ((kStage + 1) * 4);
-    const uint32_t sstage = sstage_warp + lane * ((kStage + 1) * 4);
+    // staged list entries: one row per lane
+    const uint32_t sstage_warp = smem_u32(smem + kTableBytes + kLutBytes + kRingBytes) + (threadIdx.x & ~31u) * kStageRow;
+#if EF_K1A_ES16
+    const uint32_t sstage_bias = smem_u32(smem + kTableBytes + kLutBytes + kRingBytes) - (kStageRow / 16) * smem_u32(smem + kTableBytes + kLutBytes);
+#define EF_SSTAGE (s.br.sring * (kStageRow / 16) + sstage_bias)      /* = stage base + thread * kStageRow (sring = ring base + thread * 16) */
+#else
+    const uint32_t sstage = sstage_warp + lane * kStageRow;
+#define EF_SSTAGE sstage
+#endif
     bool active = false, exhausted = false, busy = false;
     // the macroblock in flight: info word under construction (bit 0 set = a record is owed), entry count |
     // skip run << 16, motion vector, record slot
@@ -565,7 +575,7 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
 #if EF_PROBE_NOSTORE                                                  /* bottleneck probe (wrong output): only entries nobody produces are stored */
         if (ent == 0x12345678u) s.wptr[cnt] = ent;
 #else
-        if (kStage > 0 && cnt < (uint32_t)kStage) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sstage + cnt * 4), "r"(ent) : "memory");
+        if (kStage > 0 && cnt < (uint32_t)kStage) asm volatile("st.shared.u32 [%0], %1;" ::"r"(EF_SSTAGE + cnt * 4), "r"(ent) : "memory");
         else s.wptr[cnt] = ent;
 #endif
         cnt++;
@@ -591,7 +601,7 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
                         const uint64_t lb = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)li_mine, src) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(li_mine >> 32), src) << 32);
                         if (lane < c) {
                             uint32_t v;
-                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(srow + (uint32_t)src * ((kStage + 1) * 4)) : "memory");
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(srow + (uint32_t)src * kStageRow) : "memory");
                             D.coef[lb + lane] = v;
                         }
                     }
@@ -605,7 +615,7 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
                     const uint64_t lb = (uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)li_mine, src) | ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(li_mine >> 32), src) << 32);
                     for (uint32_t j = lane; j < c; j += 32) {
                         uint32_t v;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sstage_warp + (uint32_t)src * ((kStage + 1) * 4) + j * 4) : "memory");
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sstage_warp + (uint32_t)src * kStageRow + j * 4) : "memory");
                         D.coef[lb + j] = v;
                     }
                 }
@@ -687,6 +697,7 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
         // end of block folded in; dequantised on the spot (table word of the scan position: shared memory for the default
         // matrices, the stream's own table in HBM otherwise) or, with EF_K1B_DEQUANT, stored as a raw token
         const int qoff = intra ? 0 : 64, kq = intra ? 0 : 1;
+        const uint32_t* const qrow = s.qzp + qoff;               // table words of this macroblock's matrix, by scan position
         for (;;) {
             const unsigned bmask = __ballot_sync(0xFFFFFFFFu, busy);
             if (!bmask) break;
@@ -712,7 +723,7 @@ ef_parse_kernel(const __grid_constant__ EfDev D, int pic0, int n_pics)   // the 
 #if EF_K1B_DEQUANT
                             put_entry(blk24 | ((uint32_t)n << 21) | ((uint32_t)sy.lvl & 0xFFFFu));
 #else
-                            put_entry(ef_coef_entry(s.qzp[qoff + n], sy.lvl, s.qscale, kq, blk24));
+                            put_entry(ef_coef_entry(qrow[n], sy.lvl, s.qscale, kq, blk24));
 #endif
                             n++;
                             if (len <= 30 && ((w << len) >> 30) == 2u) { len += 2; block_done = true; }   // '10' follows: end of block
